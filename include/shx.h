@@ -1,0 +1,190 @@
+/* shx -- B200-native erosion hot path for SimpleHydrology worlds.  C ABI.
+ *
+ * The reference has no plugin/FFI layer; its seam is the static C++ call
+ * World::erode(int cycles) (reference source/world.h:33,54-88; called from
+ * SimpleHydrology.cpp:319) operating on the global cell pool
+ * (SimpleHydrology.cpp:11,36; source/cellpool.h:102-145,207-220) and the static
+ * parameter sets (source/water.h:43-50, source/world.h:42-44).  This header is
+ * what a binding for that seam needs: plain pointers and sizes, no CUDA or torch
+ * types.  INTEGRATION.md shows the adaptor a maintainer would drop into
+ * SimpleHydrology.cpp (simplehydrology_b200/host/shx_world.hpp).
+ *
+ * All calls are blocking unless named *_async, one context per map (or per row
+ * strip of a map), not thread-safe -- the same contract as the reference, which is
+ * single-threaded and non-reentrant (world.h:111 static scratch, global rand()).
+ * There is no CPU fallback: every entry point fails with SHX_ERR_CUDA when no
+ * sm_100 device is usable.
+ */
+#ifndef SHX_H
+#define SHX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHX_VERSION 100
+
+/* error codes (0 = ok).  The reference reports no errors at all (OOB lookups
+ * return NULL / 0.0f / false: cellpool.h:90-94,421-443, water.h:62-68); those
+ * in-simulation cases keep the reference's silent behaviour, the codes below are
+ * for misuse of the boundary itself. */
+enum {
+  SHX_OK = 0,
+  SHX_ERR_ARG = -1,       /* null pointer, bad size, unsupported parameter (lodsize != 1) */
+  SHX_ERR_CUDA = -2,      /* CUDA runtime failure; shx_last_error() has the text */
+  SHX_ERR_RANGE = -3,     /* a height does not fit the Q5.26 fixed point (|h| >= 32) */
+  SHX_ERR_MODE = -4,      /* call not available in this context's mode */
+  SHX_ERR_CAPACITY = -5,  /* more drops than the context was sized for */
+  SHX_ERR_NOMEM = -6
+};
+
+/* == quad::cell, cellpool.h:207-220: 8 x f32 = 32 B in this order.  Host buffers are
+ * the reference's pool layout: node (x/tilesize)*mapsize + (y/tilesize) owns a
+ * contiguous tilesize^2 slice (cellpool.h:327-336), x-major inside the tile
+ * (include/math.h:11-14). */
+typedef struct {
+  float height, discharge, momentumx, momentumy;
+  float discharge_track, momentumx_track, momentumy_track;
+  float rootdensity;
+} shx_cell;
+
+/* Drop:: statics (water.h:43-50), World:: statics (world.h:42-44) and the geometry
+ * constants that are compile-time in the reference (cellpool.h:165-179). */
+typedef struct {
+  float maxAge, minVol, evapRate, depositionRate, entrainment, gravity, momentumTransfer;
+  float lrate, maxdiff, settling;
+  int mapscale, tilesize, mapsize, lodsize;
+} shx_params;
+
+/* struct Drop, water.h:12-39 ({age,pos,speed,volume,sediment} = 28 B) plus a status
+ * word; also the record handed between row strips. */
+typedef struct {
+  float px, py, sx, sy, volume, sediment;
+  int age;
+  int flags; /* SHX_DROP_* */
+} shx_drop;
+
+enum {
+  SHX_DROP_ALIVE = 1,
+  SHX_DROP_CASCADE = 2,      /* World::cascade(pos) of the last step still owed (water.h:151) */
+  SHX_DROP_DONE_AGE = 4,     /* water.h:74-77 */
+  SHX_DROP_DONE_VOL = 8,     /* water.h:79-82 */
+  SHX_DROP_DONE_OOB = 16,    /* water.h:139-142 */
+  SHX_DROP_REJECTED = 32,    /* world.h:71-72 */
+  SHX_DROP_DONE_NULL = 64,   /* water.h:62-68 */
+  SHX_DROP_MIGRATE_LO = 128, /* left this strip towards smaller x */
+  SHX_DROP_MIGRATE_HI = 256
+};
+
+/* Counters of one call.  fx_* are exact integers: heights in Q5.26 (2^-26 units),
+ * sediment sums in Q31.32.  Ledger identity (tests/test_ledger.py):
+ *   sum(height_after) - sum(height_before) == fx_deposited - fx_eroded   (exactly, in Q5.26) */
+typedef struct {
+  uint64_t spawned, rejected, steps, term_age, term_vol, term_oob, cascade_transfers, phases;
+  int64_t fx_eroded, fx_deposited;
+  int64_t fx_sed_oob_lost, fx_sed_deposited, fx_sed_inflation;
+  uint64_t migrated_lo, migrated_hi;
+  uint64_t launches; /* kernels launched by this call */
+} shx_stats;
+
+#define SHX_HEIGHT_FRAC_BITS 26
+#define SHX_TRACK_FRAC_BITS 32
+
+enum {
+  SHX_MODE_BATCHED = 0,   /* all drops of a call advance in lock step; integer atomics; deterministic */
+  SHX_MODE_SEQUENTIAL = 1 /* one drop after another in fp32, operation for operation the reference
+                             (parity anchor; one GPU thread, slow by construction) */
+};
+
+typedef struct {
+  int device;          /* CUDA ordinal */
+  int mode;            /* SHX_MODE_* */
+  int row0, row1;      /* owned global rows [row0,row1) (x range); 0,0 = whole map */
+  int halo;            /* halo rows kept on each side of a strip (>= 2); ignored for the whole map */
+  size_t max_drops;    /* capacity of the drop buffers; 0 = maparea*1024 */
+  int block_threads;   /* 0 = choose; descend kernel CTA size */
+  int grid_blocks;     /* 0 = choose; descend kernel grid */
+} shx_config;
+
+typedef struct shx_ctx shx_ctx;
+
+/* field masks for shx_download */
+enum {
+  SHX_F_HEIGHT = 1, SHX_F_DISCHARGE = 2, SHX_F_MOMENTUM = 4, SHX_F_TRACKS = 8, SHX_F_ROOTDENSITY = 16,
+  SHX_F_ALL = 31
+};
+
+int shx_version(void);
+const char* shx_last_error(void);
+void shx_default_params(shx_params* p, int mapsize);
+void shx_default_config(shx_config* c);
+
+/* lifetime -- replaces cellpool.reserve()/the World statics' initialisation
+ * (SimpleHydrology.cpp:36, world.h:38-44) */
+int shx_create(shx_ctx** out, const shx_params* p, const shx_config* cfg /* may be NULL */);
+void shx_destroy(shx_ctx* c);
+int shx_set_params(shx_ctx* c, const shx_params* p); /* geometry must not change */
+int shx_get_params(const shx_ctx* c, shx_params* p);
+int shx_set_stream(shx_ctx* c, void* cuda_stream);    /* cudaStream_t; default: the legacy default stream */
+int shx_sync(shx_ctx* c);
+
+/* optional: page-lock the caller's pool so up/downloads are true async DMA */
+int shx_host_register(void* ptr, size_t bytes);
+int shx_host_unregister(void* ptr);
+
+/* map transfer.  `pool` is the whole tiled AoS pool (mapsize^2*tilesize^2 cells) even for
+ * a strip context, which picks its rows (+halo).  The caller keeps ownership. */
+int shx_upload(shx_ctx* c, const shx_cell* pool, size_t ncells);
+int shx_download(shx_ctx* c, shx_cell* pool, size_t ncells, unsigned field_mask);
+int shx_download_async(shx_ctx* c, shx_cell* pool, size_t ncells, unsigned field_mask);
+
+/* == World::erode(cycles), world.h:54-88: reset tracks, `cycles` drops per node, EMA.
+ * rand() is replaced by a counter-based hash keyed (seed, call counter, node, i). */
+int shx_erode(shx_ctx* c, int cycles, uint64_t seed, shx_stats* out /* may be NULL */);
+int shx_erode_async(shx_ctx* c, int cycles, uint64_t seed); /* no host sync; stats via shx_read_stats */
+int shx_read_stats(shx_ctx* c, shx_stats* out);             /* syncs; stats of the last *_async call */
+/* same with explicit spawn points (x,y pairs, world coordinates) -- parity mode */
+int shx_erode_spawnlist(shx_ctx* c, const float* xy, size_t ndrops, shx_stats* out);
+/* one drop, state after every Drop::descend call: 7 floats {age,pos.x,pos.y,speed.x,speed.y,volume,sediment} */
+int shx_trace_drop(shx_ctx* c, float x, float y, float* trace7, int max_steps, int* nsteps);
+
+/* the pieces of erode, for tests and for the strip orchestration */
+int shx_reset_tracks(shx_ctx* c);                                           /* world.h:56-61 */
+int shx_ema(shx_ctx* c);                                                    /* world.h:81-86 */
+int shx_spawn(shx_ctx* c, int cycles, uint64_t seed, uint64_t epoch, float* xy_out /* host, may be NULL */, size_t* n);
+int shx_run_drops(shx_ctx* c, shx_drop* drops /* host, in/out */, size_t n, shx_stats* out);
+
+/* sparse push of Plant::root stamps (vegetation.h:87-118): rootdensity[x,y] += delta */
+int shx_add_rootdensity(shx_ctx* c, const int* xy, const float* delta, size_t n);
+
+/* device-side seeded synthetic terrain (value-noise fBm normalised to [0,1]); other fields zeroed */
+int shx_synth_terrain(shx_ctx* c, uint32_t seed);
+
+/* raw device state, planar x*size+y over the stored rows (tests: bit-exact comparison with the
+ * lock-step oracle).  Any pointer may be NULL.  hq: Q5.26 planes; field4: discharge, momentumx,
+ * momentumy, rootdensity; track4: Q31.32 discharge, momentumx, momentumy, pad. */
+int shx_download_raw(shx_ctx* c, int32_t* hq0, int32_t* hq1, float* field4, int64_t* track4);
+int shx_stored_rows(const shx_ctx* c, int* xlo, int* nrows);
+
+/* ---- row-strip exchange (multi-GPU): buffers are DEVICE pointers owned by the caller
+ * (e.g. torch tensors); the transport between ranks is the caller's (NCCL send/recv or P2P). */
+/* height deltas this strip accumulated in its halo rows since the last refresh: `halo`*size int32 per side */
+int shx_strip_pack_halo_delta(shx_ctx* c, int32_t* dev_lo, int32_t* dev_hi);
+/* add a neighbour's halo deltas onto the owned boundary rows (lo: rows row0.., hi: rows ..row1) */
+int shx_strip_apply_halo_delta(shx_ctx* c, const int32_t* dev_from_lo, const int32_t* dev_from_hi);
+/* current owned boundary rows, to refresh the neighbour's halo copy: `halo`*size int32 per side */
+int shx_strip_pack_boundary(shx_ctx* c, int32_t* dev_lo, int32_t* dev_hi);
+int shx_strip_set_halo(shx_ctx* c, const int32_t* dev_lo, const int32_t* dev_hi);
+/* drops that left the strip during the last run: compacted into dev_lo/dev_hi (capacity cap each);
+ * counts are written to the two host ints (syncs) */
+int shx_strip_pack_migrants(shx_ctx* c, shx_drop* dev_lo, shx_drop* dev_hi, size_t cap, int* n_lo, int* n_hi);
+/* continue drops received from neighbours (device buffer) until they finish or leave again */
+int shx_strip_run_device_drops(shx_ctx* c, const shx_drop* dev_drops, size_t n, shx_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHX_H */
