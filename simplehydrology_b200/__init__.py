@@ -1,0 +1,276 @@
+"""simplehydrology_b200 -- B200-native erosion hot path for SimpleHydrology worlds.
+
+Python is only the test / benchmark harness here: the product is the C-ABI CUDA library
+(include/shx.h -> simplehydrology_b200/libshx.so) and the C++ host adaptor
+(simplehydrology_b200/host/shx_world.hpp).  This module binds the C ABI with ctypes and mirrors
+the reference's names (World.erode(cycles), Drop / World parameter names).  It never falls
+back to a CPU path: a missing library or GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libshx.so")
+
+# == quad::cell (reference source/cellpool.h:207-220)
+CELL_DTYPE = np.dtype(
+    [(n, np.float32) for n in ("height", "discharge", "momentumx", "momentumy",
+                               "discharge_track", "momentumx_track", "momentumy_track", "rootdensity")])
+# == struct Drop (reference source/water.h:12-39) + status word
+DROP_DTYPE = np.dtype([("px", np.float32), ("py", np.float32), ("sx", np.float32), ("sy", np.float32),
+                       ("volume", np.float32), ("sediment", np.float32), ("age", np.int32), ("flags", np.int32)])
+
+MODE_BATCHED, MODE_SEQUENTIAL = 0, 1
+F_HEIGHT, F_DISCHARGE, F_MOMENTUM, F_TRACKS, F_ROOTDENSITY, F_ALL = 1, 2, 4, 8, 16, 31
+DROP_ALIVE, DROP_CASCADE, DROP_DONE_AGE, DROP_DONE_VOL, DROP_DONE_OOB = 1, 2, 4, 8, 16
+DROP_REJECTED, DROP_DONE_NULL, DROP_MIGRATE_LO, DROP_MIGRATE_HI = 32, 64, 128, 256
+HEIGHT_FRAC_BITS, TRACK_FRAC_BITS = 26, 32
+
+
+class ShxError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__(f"shx error {code}: {text}")
+        self.code = code
+
+
+class Params(C.Structure):
+    """Drop:: statics (water.h:43-50), World:: statics (world.h:42-44), geometry (cellpool.h:165-179)"""
+    _fields_ = [(n, C.c_float) for n in ("maxAge", "minVol", "evapRate", "depositionRate", "entrainment", "gravity",
+                                         "momentumTransfer", "lrate", "maxdiff", "settling")] + \
+               [(n, C.c_int) for n in ("mapscale", "tilesize", "mapsize", "lodsize")]
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int), ("mode", C.c_int), ("row0", C.c_int), ("row1", C.c_int), ("halo", C.c_int),
+                ("max_drops", C.c_size_t), ("block_threads", C.c_int), ("grid_blocks", C.c_int)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("spawned", "rejected", "steps", "term_age", "term_vol", "term_oob",
+                                          "cascade_transfers", "phases")] + \
+               [(n, C.c_int64) for n in ("fx_eroded", "fx_deposited", "fx_sed_oob_lost", "fx_sed_deposited",
+                                         "fx_sed_inflation")] + \
+               [(n, C.c_uint64) for n in ("migrated_lo", "migrated_hi", "launches")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+_lib = None
+
+
+def lib():
+    """load libshx.so; raises if it has not been built (no fallback of any kind)"""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ShxError(-2, f"{LIB_PATH} is missing: run `python -m simplehydrology_b200.build` "
+                           "(the CUDA library is the only implementation)")
+    L = C.CDLL(LIB_PATH)
+    vp, sz, u64 = C.c_void_p, C.c_size_t, C.c_uint64
+    L.shx_last_error.restype = C.c_char_p
+    L.shx_default_params.argtypes = [C.POINTER(Params), C.c_int]
+    L.shx_default_params.restype = None
+    L.shx_default_config.argtypes = [C.POINTER(Config)]
+    L.shx_default_config.restype = None
+    L.shx_create.argtypes = [C.POINTER(vp), C.POINTER(Params), C.POINTER(Config)]
+    L.shx_destroy.argtypes = [vp]
+    L.shx_destroy.restype = None
+    L.shx_set_params.argtypes = [vp, C.POINTER(Params)]
+    L.shx_get_params.argtypes = [vp, C.POINTER(Params)]
+    L.shx_set_stream.argtypes = [vp, vp]
+    L.shx_sync.argtypes = [vp]
+    L.shx_host_register.argtypes = [vp, sz]
+    L.shx_host_unregister.argtypes = [vp]
+    L.shx_upload.argtypes = [vp, vp, sz]
+    L.shx_download.argtypes = [vp, vp, sz, C.c_uint]
+    L.shx_download_async.argtypes = [vp, vp, sz, C.c_uint]
+    L.shx_erode.argtypes = [vp, C.c_int, u64, C.POINTER(Stats)]
+    L.shx_erode_async.argtypes = [vp, C.c_int, u64]
+    L.shx_read_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.shx_erode_spawnlist.argtypes = [vp, vp, sz, C.POINTER(Stats)]
+    L.shx_trace_drop.argtypes = [vp, C.c_float, C.c_float, vp, C.c_int, C.POINTER(C.c_int)]
+    L.shx_reset_tracks.argtypes = [vp]
+    L.shx_ema.argtypes = [vp]
+    L.shx_spawn.argtypes = [vp, C.c_int, u64, u64, vp, C.POINTER(sz)]
+    L.shx_run_drops.argtypes = [vp, vp, sz, C.POINTER(Stats)]
+    L.shx_add_rootdensity.argtypes = [vp, vp, vp, sz]
+    L.shx_synth_terrain.argtypes = [vp, C.c_uint32]
+    L.shx_download_raw.argtypes = [vp, vp, vp, vp, vp]
+    L.shx_stored_rows.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.shx_strip_pack_halo_delta.argtypes = [vp, vp, vp]
+    L.shx_strip_apply_halo_delta.argtypes = [vp, vp, vp]
+    L.shx_strip_pack_boundary.argtypes = [vp, vp, vp]
+    L.shx_strip_set_halo.argtypes = [vp, vp, vp]
+    L.shx_strip_pack_migrants.argtypes = [vp, vp, vp, sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.shx_strip_run_device_drops.argtypes = [vp, vp, sz, C.POINTER(Stats)]
+    _lib = L
+    return L
+
+
+def default_params(mapsize=1):
+    p = Params()
+    lib().shx_default_params(C.byref(p), mapsize)
+    return p
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None else None
+
+
+class World:
+    """Device-resident world; `erode(cycles)` is the reference's World::erode (world.h:54-88)."""
+
+    def __init__(self, params=None, mapsize=1, mode=MODE_BATCHED, device=0, row0=0, row1=0, halo=2, max_drops=0,
+                 block_threads=0, grid_blocks=0):
+        self.L = lib()
+        self.params = params if params is not None else default_params(mapsize)
+        cfg = Config()
+        self.L.shx_default_config(C.byref(cfg))
+        cfg.device, cfg.mode, cfg.row0, cfg.row1, cfg.halo = device, mode, row0, row1, halo
+        cfg.max_drops, cfg.block_threads, cfg.grid_blocks = max_drops, block_threads, grid_blocks
+        self.cfg = cfg
+        self.size = self.params.mapsize * self.params.tilesize
+        self.ncells = self.size * self.size
+        h = C.c_void_p()
+        self._h = None
+        self._check(self.L.shx_create(C.byref(h), C.byref(self.params), C.byref(cfg)))
+        self._h = h
+
+    # -- plumbing
+    def _check(self, rc):
+        if rc != 0:
+            raise ShxError(rc, self.L.shx_last_error().decode())
+
+    def close(self):
+        if self._h:
+            self.L.shx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_stream(self, cuda_stream_handle):
+        self._check(self.L.shx_set_stream(self._h, C.c_void_p(cuda_stream_handle)))
+
+    def sync(self):
+        self._check(self.L.shx_sync(self._h))
+
+    def set_params(self, params):
+        self._check(self.L.shx_set_params(self._h, C.byref(params)))
+        self.params = params
+
+    def stored_rows(self):
+        a, b = C.c_int(), C.c_int()
+        self._check(self.L.shx_stored_rows(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    # -- map transfer (tiled AoS pool, the reference's host layout)
+    def upload(self, cells):
+        assert cells.dtype == CELL_DTYPE and cells.flags.c_contiguous
+        self._check(self.L.shx_upload(self._h, cells.ctypes.data, cells.size))
+
+    def download(self, out=None, mask=F_ALL, asynchronous=False):
+        if out is None:
+            out = np.zeros(self.ncells, CELL_DTYPE)
+        fn = self.L.shx_download_async if asynchronous else self.L.shx_download
+        self._check(fn(self._h, out.ctypes.data, out.size, mask))
+        return out
+
+    def download_raw(self, planes=True, field=True, track=True):
+        _, nrows = self.stored_rows()
+        shape = (nrows, self.size)
+        h0 = np.zeros(shape, np.int32) if planes else None
+        h1 = np.zeros(shape, np.int32) if planes else None
+        f = np.zeros(shape + (4,), np.float32) if field else None
+        t = np.zeros(shape + (4,), np.int64) if track else None
+        self._check(self.L.shx_download_raw(self._h, _ptr(h0), _ptr(h1), _ptr(f), _ptr(t)))
+        return h0, h1, f, t
+
+    def synth_terrain(self, seed):
+        self._check(self.L.shx_synth_terrain(self._h, seed))
+
+    # -- the hot path
+    def erode(self, cycles, seed=0):
+        st = Stats()
+        self._check(self.L.shx_erode(self._h, cycles, seed, C.byref(st)))
+        return st
+
+    def erode_async(self, cycles, seed=0):
+        self._check(self.L.shx_erode_async(self._h, cycles, seed))
+
+    def read_stats(self):
+        st = Stats()
+        self._check(self.L.shx_read_stats(self._h, C.byref(st)))
+        return st
+
+    def erode_spawnlist(self, xy):
+        xy = np.ascontiguousarray(xy, np.float32)
+        st = Stats()
+        self._check(self.L.shx_erode_spawnlist(self._h, xy.ctypes.data, xy.size // 2, C.byref(st)))
+        return st
+
+    def trace_drop(self, x, y, max_steps=1024):
+        tr = np.zeros((max_steps, 7), np.float32)
+        n = C.c_int(0)
+        self._check(self.L.shx_trace_drop(self._h, x, y, tr.ctypes.data, max_steps, C.byref(n)))
+        return tr[:n.value].copy()
+
+    def reset_tracks(self):
+        self._check(self.L.shx_reset_tracks(self._h))
+
+    def ema(self):
+        self._check(self.L.shx_ema(self._h))
+
+    def spawn(self, cycles, seed, epoch):
+        n = C.c_size_t(0)
+        cap = self.params.mapsize ** 2 * cycles
+        xy = np.zeros((max(cap, 1), 2), np.float32)
+        self._check(self.L.shx_spawn(self._h, cycles, seed, epoch, xy.ctypes.data, C.byref(n)))
+        return xy[:n.value].copy()
+
+    def run_drops(self, drops):
+        assert drops.dtype == DROP_DTYPE and drops.flags.c_contiguous
+        st = Stats()
+        self._check(self.L.shx_run_drops(self._h, drops.ctypes.data, drops.size, C.byref(st)))
+        return st
+
+    def add_rootdensity(self, xy, delta):
+        xy = np.ascontiguousarray(xy, np.int32)
+        delta = np.ascontiguousarray(delta, np.float32)
+        self._check(self.L.shx_add_rootdensity(self._h, xy.ctypes.data, delta.ctypes.data, delta.size))
+
+    # -- strip exchange (device pointers as ints)
+    def strip_pack_halo_delta(self, lo, hi):
+        self._check(self.L.shx_strip_pack_halo_delta(self._h, lo, hi))
+
+    def strip_apply_halo_delta(self, from_lo, from_hi):
+        self._check(self.L.shx_strip_apply_halo_delta(self._h, from_lo, from_hi))
+
+    def strip_pack_boundary(self, lo, hi):
+        self._check(self.L.shx_strip_pack_boundary(self._h, lo, hi))
+
+    def strip_set_halo(self, lo, hi):
+        self._check(self.L.shx_strip_set_halo(self._h, lo, hi))
+
+    def strip_pack_migrants(self, lo, hi, cap):
+        a, b = C.c_int(), C.c_int()
+        self._check(self.L.shx_strip_pack_migrants(self._h, lo, hi, cap, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def strip_run_device_drops(self, dev_ptr, n, want_stats=True):
+        st = Stats()
+        self._check(self.L.shx_strip_run_device_drops(self._h, dev_ptr, n, C.byref(st) if want_stats else None))
+        return st

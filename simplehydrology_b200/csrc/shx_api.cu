@@ -1,0 +1,716 @@
+// shx C ABI (include/shx.h): context, transfers and kernel launches.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false -prec-div=true -prec-sqrt=true
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "shx_kernels.cuh"
+
+using namespace shx;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* what) {
+  g_err = what ? what : "";
+  return code;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      char b__[512];                                                                          \
+      snprintf(b__, sizeof b__, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return fail(SHX_ERR_CUDA, b__);                                                         \
+    }                                                                                         \
+  } while (0)
+
+struct shx_ctx {
+  shx_params p;
+  shx_config cfg;
+  int size = 0;
+  MapView m{};
+  size_t stored_cells = 0, owned_cells = 0;
+  int halo_lo = 0, halo_hi = 0;  // halo rows actually present on each side
+  shx_drop* d_drops = nullptr;
+  size_t max_drops = 0;
+  float* d_xy = nullptr;
+  GridBar* d_bar = nullptr;
+  unsigned long long* d_stats = nullptr;
+  unsigned long long* h_stats = nullptr;  // pinned
+  int* d_flags = nullptr;                 // [0] range error, [1] trace_n
+  int* h_flags = nullptr;                 // pinned
+  float* d_trace = nullptr;
+  int trace_cap = 1024;
+  unsigned* d_u32 = nullptr;  // [0..1] min/max, [2..3] migrant counts
+  int32_t* d_halo_ref[2] = {nullptr, nullptr};
+  shx_cell* d_stage = nullptr;
+  cudaStream_t stream = nullptr;  // legacy default stream unless set
+  int sm_count = 0;
+  uint64_t epoch = 0;
+  uint64_t launches = 0;
+  size_t last_n = 0;         // drops of the last run still sitting in d_drops
+  int cap_blocks_big = 0;    // co-resident CTAs of the 64-register instantiation at block_big
+  int block_big = 256;
+};
+
+static StepParams step_params(const shx_params& p) {
+  StepParams s;
+  s.maxAge = p.maxAge; s.minVol = p.minVol; s.evapRate = p.evapRate; s.depositionRate = p.depositionRate;
+  s.entrainment = p.entrainment; s.gravity = p.gravity; s.momentumTransfer = p.momentumTransfer;
+  s.maxdiff = p.maxdiff; s.settling = p.settling; s.lod = (float)p.lodsize; s.mapscale = (float)p.mapscale;
+  s.lrate = p.lrate;
+  return s;
+}
+
+static bool sequential(const shx_ctx* c) { return c->cfg.mode == SHX_MODE_SEQUENTIAL; }
+
+static int grid_for(const shx_ctx* c, size_t n, int block = 256) {
+  const size_t want = (n + block - 1) / block;
+  const size_t cap = (size_t)c->sm_count * 8;
+  return (int)std::max<size_t>(1, std::min(want, cap));
+}
+
+// the two instantiations: one CTA of up to 1024 threads (small batches: the barrier is a plain
+// __syncthreads) and the occupancy-oriented one (<= 64 registers, 1024 threads per SM)
+#define KERNEL_SMALL descend_lockstep_kernel<1024, 1>
+#define KERNEL_BIG descend_lockstep_kernel<256, 4>
+
+extern "C" {
+
+int shx_version(void) { return SHX_VERSION; }
+const char* shx_last_error(void) { return g_err.c_str(); }
+
+void shx_default_params(shx_params* p, int mapsize) {
+  if (!p) return;
+  p->evapRate = 0.001f;        // water.h:43
+  p->depositionRate = 0.1f;    // water.h:44
+  p->minVol = 0.01f;           // water.h:45
+  p->maxAge = 500.0f;          // water.h:46
+  p->entrainment = 10.0f;      // water.h:48
+  p->gravity = 1.0f;           // water.h:49
+  p->momentumTransfer = 1.0f;  // water.h:50
+  p->lrate = 0.1f;             // world.h:42
+  p->maxdiff = 0.01f;          // world.h:43
+  p->settling = 0.8f;          // world.h:44
+  p->mapscale = 80;            // cellpool.h:165
+  p->tilesize = 512;           // cellpool.h:167
+  p->mapsize = mapsize;        // cellpool.h:171
+  p->lodsize = 1;              // cellpool.h:178
+}
+
+void shx_default_config(shx_config* c) {
+  if (!c) return;
+  memset(c, 0, sizeof(*c));
+  c->mode = SHX_MODE_BATCHED;
+  c->halo = 2;
+}
+
+void shx_destroy(shx_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  cudaFree(c->m.h[0]); cudaFree(c->m.h[1]); cudaFree(c->m.field); cudaFree(c->m.track);
+  cudaFree(c->d_drops); cudaFree(c->d_xy); cudaFree(c->d_bar); cudaFree(c->d_stats); cudaFree(c->d_flags);
+  cudaFree(c->d_trace); cudaFree(c->d_u32); cudaFree(c->d_halo_ref[0]); cudaFree(c->d_halo_ref[1]);
+  cudaFree(c->d_stage);
+  if (c->h_stats) cudaFreeHost(c->h_stats);
+  if (c->h_flags) cudaFreeHost(c->h_flags);
+  delete c;
+}
+
+int shx_create(shx_ctx** out, const shx_params* p, const shx_config* cfg_in) {
+  if (!out || !p) return fail(SHX_ERR_ARG, "shx_create: null argument");
+  *out = nullptr;
+  if (p->lodsize != 1) return fail(SHX_ERR_ARG, "only lodsize == 1 is supported (cellpool.h:178)");
+  if (p->mapsize < 1 || p->tilesize < 4 || (long long)p->mapsize * p->tilesize > 46340)
+    return fail(SHX_ERR_ARG, "bad geometry");
+  shx_config cfg;
+  if (cfg_in) cfg = *cfg_in; else shx_default_config(&cfg);
+  const int size = p->mapsize * p->tilesize;
+  if (cfg.row0 == 0 && cfg.row1 == 0) cfg.row1 = size;
+  if (cfg.row0 < 0 || cfg.row1 > size || cfg.row0 >= cfg.row1) return fail(SHX_ERR_ARG, "bad strip rows");
+  const bool whole = cfg.row0 == 0 && cfg.row1 == size;
+  if (!whole && cfg.halo < 2) return fail(SHX_ERR_ARG, "strip halo must be >= 2 rows");
+  if (!whole && cfg.mode == SHX_MODE_SEQUENTIAL) return fail(SHX_ERR_MODE, "sequential mode is whole-map only");
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(SHX_ERR_CUDA, "no CUDA device: shx has no CPU fallback");
+  if (cfg.device < 0 || cfg.device >= ndev) return fail(SHX_ERR_ARG, "bad device ordinal");
+  CU(cudaSetDevice(cfg.device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, cfg.device));
+  if (prop.major < 10) return fail(SHX_ERR_CUDA, "shx kernels are built for sm_100a only");
+
+  shx_ctx* c = new (std::nothrow) shx_ctx();
+  if (!c) return fail(SHX_ERR_NOMEM, "host allocation failed");
+  c->p = *p;
+  c->cfg = cfg;
+  c->size = size;
+  c->sm_count = prop.multiProcessorCount;
+  c->halo_lo = whole ? 0 : std::min(cfg.halo, cfg.row0);
+  c->halo_hi = whole ? 0 : std::min(cfg.halo, size - cfg.row1);
+  c->m.size = size;
+  c->m.xlo = cfg.row0 - c->halo_lo;
+  c->m.nrows = (cfg.row1 + c->halo_hi) - c->m.xlo;
+  c->m.row0 = cfg.row0;
+  c->m.row1 = cfg.row1;
+  c->stored_cells = (size_t)c->m.nrows * size;
+  c->owned_cells = (size_t)(cfg.row1 - cfg.row0) * size;
+  c->max_drops = cfg.max_drops ? cfg.max_drops : (size_t)p->mapsize * p->mapsize * 1024;
+  const size_t tile_cells = (size_t)p->tilesize * p->tilesize;
+
+#define ALLOC(ptr, bytes)                                                  \
+  do {                                                                     \
+    if (cudaMalloc((void**)&(ptr), (bytes)) != cudaSuccess) {              \
+      shx_destroy(c);                                                      \
+      return fail(SHX_ERR_NOMEM, "cudaMalloc failed for " #ptr);           \
+    }                                                                      \
+  } while (0)
+  ALLOC(c->m.h[0], c->stored_cells * sizeof(int32_t));
+  ALLOC(c->m.h[1], c->stored_cells * sizeof(int32_t));
+  ALLOC(c->m.field, c->stored_cells * sizeof(float4));
+  ALLOC(c->m.track, c->stored_cells * sizeof(Track));
+  ALLOC(c->d_drops, c->max_drops * sizeof(shx_drop));
+  ALLOC(c->d_xy, c->max_drops * 2 * sizeof(float));
+  ALLOC(c->d_bar, sizeof(GridBar));
+  ALLOC(c->d_stats, ST_COUNT * 8);
+  ALLOC(c->d_flags, 4 * sizeof(int));
+  ALLOC(c->d_trace, (size_t)c->trace_cap * 7 * sizeof(float));
+  ALLOC(c->d_u32, 4 * sizeof(unsigned));
+  ALLOC(c->d_stage, tile_cells * sizeof(shx_cell));
+  if (!whole) {
+    ALLOC(c->d_halo_ref[0], (size_t)std::max(1, c->halo_lo) * size * sizeof(int32_t));
+    ALLOC(c->d_halo_ref[1], (size_t)std::max(1, c->halo_hi) * size * sizeof(int32_t));
+  }
+#undef ALLOC
+  if (cudaMallocHost((void**)&c->h_stats, ST_COUNT * 8) != cudaSuccess ||
+      cudaMallocHost((void**)&c->h_flags, 4 * sizeof(int)) != cudaSuccess) {
+    shx_destroy(c);
+    return fail(SHX_ERR_NOMEM, "cudaMallocHost failed");
+  }
+  cudaMemset(c->m.h[0], 0, c->stored_cells * sizeof(int32_t));
+  cudaMemset(c->m.h[1], 0, c->stored_cells * sizeof(int32_t));
+  cudaMemset(c->m.field, 0, c->stored_cells * sizeof(float4));
+  cudaMemset(c->m.track, 0, c->stored_cells * sizeof(Track));
+  cudaMemset(c->d_stats, 0, ST_COUNT * 8);
+  cudaMemset(c->d_flags, 0, 4 * sizeof(int));
+
+  c->block_big = cfg.block_threads > 0 ? std::min(256, (cfg.block_threads + 31) / 32 * 32) : 256;
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, KERNEL_BIG, c->block_big, 9 * sizeof(int32_t) * c->block_big) != cudaSuccess ||
+      nb < 1) {
+    shx_destroy(c);
+    return fail(SHX_ERR_CUDA, "descend kernel does not fit on this device");
+  }
+  c->cap_blocks_big = nb * c->sm_count;
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    shx_destroy(c);
+    return fail(SHX_ERR_CUDA, "context initialisation failed");
+  }
+  *out = c;
+  return SHX_OK;
+}
+
+int shx_set_params(shx_ctx* c, const shx_params* p) {
+  if (!c || !p) return fail(SHX_ERR_ARG, "null argument");
+  if (p->mapsize != c->p.mapsize || p->tilesize != c->p.tilesize || p->lodsize != 1)
+    return fail(SHX_ERR_ARG, "geometry cannot change after shx_create");
+  c->p = *p;
+  return SHX_OK;
+}
+
+int shx_get_params(const shx_ctx* c, shx_params* p) {
+  if (!c || !p) return fail(SHX_ERR_ARG, "null argument");
+  *p = c->p;
+  return SHX_OK;
+}
+
+int shx_set_stream(shx_ctx* c, void* s) {
+  if (!c) return fail(SHX_ERR_ARG, "null context");
+  c->stream = (cudaStream_t)s;
+  return SHX_OK;
+}
+
+int shx_sync(shx_ctx* c) {
+  if (!c) return fail(SHX_ERR_ARG, "null context");
+  CU(cudaSetDevice(c->cfg.device));
+  CU(cudaStreamSynchronize(c->stream));
+  return SHX_OK;
+}
+
+int shx_host_register(void* ptr, size_t bytes) {
+  if (!ptr) return fail(SHX_ERR_ARG, "null pointer");
+  CU(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  return SHX_OK;
+}
+int shx_host_unregister(void* ptr) {
+  if (!ptr) return fail(SHX_ERR_ARG, "null pointer");
+  CU(cudaHostUnregister(ptr));
+  return SHX_OK;
+}
+
+int shx_stored_rows(const shx_ctx* c, int* xlo, int* nrows) {
+  if (!c) return fail(SHX_ERR_ARG, "null context");
+  if (xlo) *xlo = c->m.xlo;
+  if (nrows) *nrows = c->m.nrows;
+  return SHX_OK;
+}
+
+// ------------------------------------------------------------------------------- transfers
+
+static int refresh_halo_ref(shx_ctx* c) {
+  for (int side = 0; side < 2; side++) {
+    const int rows = side == 0 ? c->halo_lo : c->halo_hi;
+    if (!rows || !c->d_halo_ref[side]) continue;
+    const size_t n = (size_t)rows * c->size;
+    const size_t off = side == 0 ? 0 : (size_t)(c->m.row1 - c->m.xlo) * c->size;
+    CU(cudaMemcpyAsync(c->d_halo_ref[side], c->m.h[0] + off, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
+  }
+  return SHX_OK;
+}
+
+int shx_upload(shx_ctx* c, const shx_cell* pool, size_t ncells) {
+  if (!c || !pool) return fail(SHX_ERR_ARG, "null argument");
+  if (ncells != (size_t)c->size * c->size) return fail(SHX_ERR_ARG, "pool size does not match the geometry");
+  CU(cudaSetDevice(c->cfg.device));
+  const int ts = c->p.tilesize, ms = c->p.mapsize;
+  const size_t tile_cells = (size_t)ts * ts;
+  CU(cudaMemsetAsync(c->d_flags, 0, sizeof(int), c->stream));
+  for (int ti = 0; ti < ms; ti++) {
+    if ((ti + 1) * ts <= c->m.xlo || ti * ts >= c->m.xlo + c->m.nrows) continue;
+    for (int tj = 0; tj < ms; tj++) {
+      const size_t node = (size_t)ti * ms + tj;  // cellpool.h:330
+      CU(cudaMemcpyAsync(c->d_stage, pool + node * tile_cells, tile_cells * sizeof(shx_cell), cudaMemcpyHostToDevice, c->stream));
+      TileArgs a{c->m, sequential(c) ? 1 : 0, ts, ti * ts, tj * ts, c->d_flags};
+      unpack_tile_kernel<<<grid_for(c, tile_cells), 256, 0, c->stream>>>(a, c->d_stage);
+      c->launches++;
+    }
+  }
+  CU(cudaGetLastError());
+  int rc = refresh_halo_ref(c);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (c->h_flags[0]) return fail(SHX_ERR_RANGE, "a height is outside (-31, 31): does not fit Q5.26");
+  return SHX_OK;
+}
+
+int shx_download_async(shx_ctx* c, shx_cell* pool, size_t ncells, unsigned mask) {
+  if (!c || !pool) return fail(SHX_ERR_ARG, "null argument");
+  if (ncells != (size_t)c->size * c->size) return fail(SHX_ERR_ARG, "pool size does not match the geometry");
+  mask &= SHX_F_ALL;
+  if (!mask) return SHX_OK;
+  CU(cudaSetDevice(c->cfg.device));
+  const int ts = c->p.tilesize, ms = c->p.mapsize;
+  const size_t tile_cells = (size_t)ts * ts;
+  // byte runs of the 32-byte record selected by the mask
+  bool want[8] = {(mask & SHX_F_HEIGHT) != 0, (mask & SHX_F_DISCHARGE) != 0, (mask & SHX_F_MOMENTUM) != 0,
+                  (mask & SHX_F_MOMENTUM) != 0, (mask & SHX_F_TRACKS) != 0, (mask & SHX_F_TRACKS) != 0,
+                  (mask & SHX_F_TRACKS) != 0, (mask & SHX_F_ROOTDENSITY) != 0};
+  for (int ti = 0; ti < ms; ti++) {
+    const int lx0 = std::max(c->m.row0 - ti * ts, 0), lx1 = std::min(c->m.row1 - ti * ts, ts);
+    if (lx0 >= lx1) continue;
+    for (int tj = 0; tj < ms; tj++) {
+      const size_t node = (size_t)ti * ms + tj;
+      TileArgs a{c->m, sequential(c) ? 1 : 0, ts, ti * ts, tj * ts, c->d_flags};
+      pack_tile_kernel<<<grid_for(c, tile_cells), 256, 0, c->stream>>>(a, c->d_stage);
+      c->launches++;
+      const size_t first = (size_t)lx0 * ts, count = (size_t)(lx1 - lx0) * ts;
+      char* dst = reinterpret_cast<char*>(pool + node * tile_cells + first);
+      const char* src = reinterpret_cast<const char*>(c->d_stage + first);
+      if (mask == SHX_F_ALL) {
+        CU(cudaMemcpyAsync(dst, src, count * sizeof(shx_cell), cudaMemcpyDeviceToHost, c->stream));
+      } else {
+        for (int f = 0; f < 8;) {
+          if (!want[f]) { f++; continue; }
+          int g = f;
+          while (g < 8 && want[g]) g++;
+          CU(cudaMemcpy2DAsync(dst + 4 * f, sizeof(shx_cell), src + 4 * f, sizeof(shx_cell), (size_t)4 * (g - f), count,
+                               cudaMemcpyDeviceToHost, c->stream));
+          f = g;
+        }
+      }
+    }
+  }
+  CU(cudaGetLastError());
+  return SHX_OK;
+}
+
+int shx_download(shx_ctx* c, shx_cell* pool, size_t ncells, unsigned mask) {
+  int rc = shx_download_async(c, pool, ncells, mask);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  return SHX_OK;
+}
+
+int shx_download_raw(shx_ctx* c, int32_t* hq0, int32_t* hq1, float* field4, int64_t* track4) {
+  if (!c) return fail(SHX_ERR_ARG, "null context");
+  CU(cudaSetDevice(c->cfg.device));
+  CU(cudaStreamSynchronize(c->stream));
+  if (hq0) CU(cudaMemcpy(hq0, c->m.h[0], c->stored_cells * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (hq1) CU(cudaMemcpy(hq1, c->m.h[1], c->stored_cells * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (field4) CU(cudaMemcpy(field4, c->m.field, c->stored_cells * sizeof(float4), cudaMemcpyDeviceToHost));
+  if (track4) CU(cudaMemcpy(track4, c->m.track, c->stored_cells * sizeof(Track), cudaMemcpyDeviceToHost));
+  return SHX_OK;
+}
+
+// ------------------------------------------------------------------------------- erode pieces
+
+static int fetch_stats(shx_ctx* c, shx_stats* out) {
+  CU(cudaMemcpyAsync(c->h_stats, c->d_stats, ST_COUNT * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (out) {
+    memcpy(out, c->h_stats, sizeof(shx_stats));
+    out->launches = c->launches;
+  }
+  return SHX_OK;
+}
+
+static int begin_call(shx_ctx* c) {
+  CU(cudaSetDevice(c->cfg.device));
+  c->launches = 0;
+  CU(cudaMemsetAsync(c->d_stats, 0, ST_COUNT * 8, c->stream));
+  return SHX_OK;
+}
+
+int shx_reset_tracks(shx_ctx* c) {  // world.h:56-61
+  if (!c) return fail(SHX_ERR_ARG, "null context");
+  CU(cudaSetDevice(c->cfg.device));
+  CU(cudaMemsetAsync(c->m.track, 0, c->stored_cells * sizeof(Track), c->stream));
+  return SHX_OK;
+}
+
+int shx_ema(shx_ctx* c) {  // world.h:81-86
+  if (!c) return fail(SHX_ERR_ARG, "null context");
+  CU(cudaSetDevice(c->cfg.device));
+  const size_t off = (size_t)(c->m.row0 - c->m.xlo) * c->size;
+  const int grid = (int)std::min<size_t>((c->owned_cells + 255) / 256, (size_t)c->sm_count * 16);
+  if (sequential(c))
+    ema_sequential_kernel<<<grid, 256, 0, c->stream>>>(c->m.field + off, reinterpret_cast<const float4*>(c->m.track + off),
+                                                        c->owned_cells, c->p.lrate);
+  else
+    ema_kernel<<<grid, 256, 0, c->stream>>>(c->m.field + off, c->m.track + off, c->owned_cells, c->p.lrate);
+  c->launches++;
+  CU(cudaGetLastError());
+  return SHX_OK;
+}
+
+// march n drops already in c->d_drops
+static int run_device_drops(shx_ctx* c, size_t n, bool trace) {
+  c->last_n = n;
+  if (n == 0) return SHX_OK;
+  if (n > c->max_drops) return fail(SHX_ERR_CAPACITY, "more drops than max_drops");
+  if (sequential(c)) {
+    SequentialArgs a;
+    a.h = reinterpret_cast<float*>(c->m.h[0]);
+    a.field = c->m.field;
+    a.trackf = reinterpret_cast<float4*>(c->m.track);
+    a.size = c->size;
+    a.P = step_params(c->p);
+    a.drops = c->d_drops;
+    a.ndrops = (unsigned)n;
+    a.stats = c->d_stats;
+    a.trace = trace ? c->d_trace : nullptr;
+    a.trace_cap = c->trace_cap;
+    a.trace_n = trace ? c->d_flags + 1 : nullptr;
+    descend_sequential_kernel<<<1, 1, 0, c->stream>>>(a);
+    c->launches++;
+    CU(cudaGetLastError());
+    return SHX_OK;
+  }
+  // batched: sub-batches of at most `capacity` co-resident threads, in list order
+  size_t done = 0;
+  while (done < n) {
+    const size_t left = n - done;
+    DescendArgs a;
+    a.m = c->m;
+    a.P = step_params(c->p);
+    a.drops = c->d_drops + done;
+    a.bar = c->d_bar;
+    a.stats = c->d_stats;
+    a.trace = (trace && done == 0) ? c->d_trace : nullptr;
+    a.trace_cap = c->trace_cap;
+    a.trace_n = (trace && done == 0) ? c->d_flags + 1 : nullptr;
+    CU(cudaMemsetAsync(c->d_bar, 0, sizeof(GridBar), c->stream));
+    void* args[] = {&a};
+    size_t take;
+    const bool force_grid = c->cfg.grid_blocks > 0;
+    if (left <= 1024 && !force_grid) {
+      take = left;
+      a.ndrops = (unsigned)take;
+      const int block = (int)((take + 31) / 32 * 32);
+      CU(cudaLaunchCooperativeKernel((void*)KERNEL_SMALL, dim3(1), dim3(block), args, 9 * sizeof(int32_t) * block, c->stream));
+    } else {
+      const int block = c->block_big;
+      int cap = c->cap_blocks_big;
+      if (force_grid) cap = std::min(cap, c->cfg.grid_blocks);
+      take = std::min(left, (size_t)cap * block);
+      a.ndrops = (unsigned)take;
+      const int grid = (int)((take + block - 1) / block);
+      CU(cudaLaunchCooperativeKernel((void*)KERNEL_BIG, dim3(grid), dim3(block), args, 9 * sizeof(int32_t) * block, c->stream));
+    }
+    c->launches++;
+    done += take;
+  }
+  return SHX_OK;
+}
+
+static int spawn_device(shx_ctx* c, int cycles, uint64_t seed, uint64_t epoch, size_t* n_out) {
+  const int ts = c->p.tilesize, ms = c->p.mapsize;
+  if (cycles < 0) return fail(SHX_ERR_ARG, "negative cycles");
+  if (c->m.row0 % ts || c->m.row1 % ts) return fail(SHX_ERR_ARG, "spawning needs tile-aligned strips");
+  const unsigned node0 = (unsigned)(c->m.row0 / ts) * ms, nnodes = (unsigned)((c->m.row1 - c->m.row0) / ts) * ms;
+  const size_t n = (size_t)nnodes * cycles;
+  if (n > c->max_drops) return fail(SHX_ERR_CAPACITY, "cycles*nodes exceeds max_drops");
+  *n_out = n;
+  if (!n) return SHX_OK;
+  SpawnArgs a;
+  a.hq = sequential(c) ? nullptr : c->m.h[0];
+  a.hf = sequential(c) ? reinterpret_cast<const float*>(c->m.h[0]) : nullptr;
+  a.size = c->size; a.xlo = c->m.xlo; a.tilesize = ts; a.mapsize = ms;
+  a.node0 = node0; a.nnodes = nnodes; a.cycles = cycles;
+  a.key = mix64(mix64(seed) + epoch);
+  a.drops = c->d_drops;
+  a.xy = c->d_xy;
+  a.stats = c->d_stats;
+  spawn_kernel<<<grid_for(c, n), 256, 0, c->stream>>>(a, c->m.row0, c->m.row1);
+  c->launches++;
+  CU(cudaGetLastError());
+  return SHX_OK;
+}
+
+int shx_erode_async(shx_ctx* c, int cycles, uint64_t seed) {
+  if (!c) return fail(SHX_ERR_ARG, "null context");
+  int rc = begin_call(c);
+  if (rc) return rc;
+  if ((rc = shx_reset_tracks(c))) return rc;  // world.h:56-61
+  size_t n = 0;
+  if ((rc = spawn_device(c, cycles, seed, c->epoch, &n))) return rc;  // world.h:64-74
+  c->epoch++;
+  if ((rc = run_device_drops(c, n, false))) return rc;  // world.h:76
+  return shx_ema(c);                                    // world.h:81-86
+}
+
+int shx_read_stats(shx_ctx* c, shx_stats* out) {
+  if (!c) return fail(SHX_ERR_ARG, "null context");
+  CU(cudaSetDevice(c->cfg.device));
+  return fetch_stats(c, out);
+}
+
+int shx_erode(shx_ctx* c, int cycles, uint64_t seed, shx_stats* out) {
+  int rc = shx_erode_async(c, cycles, seed);
+  if (rc) return rc;
+  return fetch_stats(c, out);
+}
+
+static int make_drops_from_xy(shx_ctx* c, const float* xy_host, size_t n) {
+  if (n > c->max_drops) return fail(SHX_ERR_CAPACITY, "more drops than max_drops");
+  if (!n) return SHX_OK;
+  CU(cudaMemcpyAsync(c->d_xy, xy_host, n * 2 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  make_drops_kernel<<<grid_for(c, n), 256, 0, c->stream>>>(
+      c->d_xy, (unsigned)n, sequential(c) ? nullptr : c->m.h[0],
+      sequential(c) ? reinterpret_cast<const float*>(c->m.h[0]) : nullptr, c->size, c->m.xlo, c->m.row0, c->m.row1,
+      c->d_drops, c->d_stats);
+  c->launches++;
+  CU(cudaGetLastError());
+  return SHX_OK;
+}
+
+int shx_erode_spawnlist(shx_ctx* c, const float* xy, size_t n, shx_stats* out) {
+  if (!c || (!xy && n)) return fail(SHX_ERR_ARG, "null argument");
+  int rc = begin_call(c);
+  if (rc) return rc;
+  if ((rc = shx_reset_tracks(c))) return rc;
+  if ((rc = make_drops_from_xy(c, xy, n))) return rc;
+  if ((rc = run_device_drops(c, n, false))) return rc;
+  if ((rc = shx_ema(c))) return rc;
+  return fetch_stats(c, out);
+}
+
+int shx_trace_drop(shx_ctx* c, float x, float y, float* trace7, int max_steps, int* nsteps) {
+  if (!c || !trace7 || !nsteps || max_steps < 1) return fail(SHX_ERR_ARG, "bad argument");
+  int rc = begin_call(c);
+  if (rc) return rc;
+  const float xy[2] = {x, y};
+  CU(cudaMemsetAsync(c->d_flags + 1, 0, sizeof(int), c->stream));
+  // no rejection here: Drop(pos) followed by while(descend()) exactly as a caller of the reference would
+  const shx_drop d = {x, y, 0.0f, 0.0f, 1.0f, 0.0f, 0, SHX_DROP_ALIVE};
+  (void)xy;
+  const int ix = (int)x, iy = (int)y;
+  if (!(x > -1.0f) || !(y > -1.0f) || ix >= c->size || iy >= c->size || ix < c->m.row0 || ix >= c->m.row1) {
+    *nsteps = 0;  // water.h:62-68: NULL node -> descend returns false immediately
+    return SHX_OK;
+  }
+  CU(cudaMemcpyAsync(c->d_drops, &d, sizeof d, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = run_device_drops(c, 1, true))) return rc;
+  CU(cudaMemcpyAsync(c->h_flags + 1, c->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  const int n = std::min(c->h_flags[1], max_steps);
+  CU(cudaMemcpy(trace7, c->d_trace, (size_t)n * 7 * sizeof(float), cudaMemcpyDeviceToHost));
+  *nsteps = n;
+  return SHX_OK;
+}
+
+int shx_spawn(shx_ctx* c, int cycles, uint64_t seed, uint64_t epoch, float* xy_out, size_t* n_out) {
+  if (!c || !n_out) return fail(SHX_ERR_ARG, "null argument");
+  int rc = begin_call(c);
+  if (rc) return rc;
+  size_t n = 0;
+  if ((rc = spawn_device(c, cycles, seed, epoch, &n))) return rc;
+  *n_out = n;
+  if (xy_out && n) CU(cudaMemcpyAsync(xy_out, c->d_xy, n * 2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return SHX_OK;
+}
+
+int shx_run_drops(shx_ctx* c, shx_drop* drops, size_t n, shx_stats* out) {
+  if (!c || (!drops && n)) return fail(SHX_ERR_ARG, "null argument");
+  if (n > c->max_drops) return fail(SHX_ERR_CAPACITY, "more drops than max_drops");
+  int rc = begin_call(c);
+  if (rc) return rc;
+  if (n) CU(cudaMemcpyAsync(c->d_drops, drops, n * sizeof(shx_drop), cudaMemcpyHostToDevice, c->stream));
+  if ((rc = run_device_drops(c, n, false))) return rc;
+  if (n) CU(cudaMemcpyAsync(drops, c->d_drops, n * sizeof(shx_drop), cudaMemcpyDeviceToHost, c->stream));
+  return fetch_stats(c, out);
+}
+
+int shx_add_rootdensity(shx_ctx* c, const int* xy, const float* delta, size_t n) {
+  if (!c || ((!xy || !delta) && n)) return fail(SHX_ERR_ARG, "null argument");
+  if (!n) return SHX_OK;
+  CU(cudaSetDevice(c->cfg.device));
+  int* d_xy = nullptr;
+  float* d_delta = nullptr;
+  CU(cudaMallocAsync((void**)&d_xy, n * 2 * sizeof(int), c->stream));
+  CU(cudaMallocAsync((void**)&d_delta, n * sizeof(float), c->stream));
+  CU(cudaMemcpyAsync(d_xy, xy, n * 2 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(d_delta, delta, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  add_rootdensity_kernel<<<1, 1, 0, c->stream>>>(c->m, d_xy, d_delta, n);
+  c->launches++;
+  CU(cudaGetLastError());
+  CU(cudaFreeAsync(d_xy, c->stream));
+  CU(cudaFreeAsync(d_delta, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return SHX_OK;
+}
+
+int shx_synth_terrain(shx_ctx* c, uint32_t seed) {
+  if (!c) return fail(SHX_ERR_ARG, "null context");
+  CU(cudaSetDevice(c->cfg.device));
+  const unsigned init[2] = {0xffffffffu, 0u};
+  CU(cudaMemcpyAsync(c->d_u32, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+  synth_minmax_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->size, seed, c->d_u32);
+  synth_fill_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->m, sequential(c) ? 1 : 0, seed, c->d_u32);
+  c->launches += 2;
+  CU(cudaGetLastError());
+  int rc = refresh_halo_ref(c);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  return SHX_OK;
+}
+
+// ------------------------------------------------------------------------------- row strips
+
+static int strip_check(shx_ctx* c) {
+  if (!c) return fail(SHX_ERR_ARG, "null context");
+  if (sequential(c)) return fail(SHX_ERR_MODE, "strips need the batched mode");
+  CU(cudaSetDevice(c->cfg.device));
+  return SHX_OK;
+}
+
+int shx_strip_pack_halo_delta(shx_ctx* c, int32_t* dev_lo, int32_t* dev_hi) {
+  int rc = strip_check(c);
+  if (rc) return rc;
+  for (int side = 0; side < 2; side++) {
+    const int rows = side == 0 ? c->halo_lo : c->halo_hi;
+    int32_t* out = side == 0 ? dev_lo : dev_hi;
+    if (!rows || !out) continue;
+    const size_t n = (size_t)rows * c->size;
+    const size_t off = side == 0 ? 0 : (size_t)(c->m.row1 - c->m.xlo) * c->size;
+    strip_halo_delta_kernel<<<grid_for(c, n), 256, 0, c->stream>>>(c->m.h[0] + off, c->d_halo_ref[side], out, n);
+    c->launches++;
+  }
+  CU(cudaGetLastError());
+  return SHX_OK;
+}
+
+int shx_strip_apply_halo_delta(shx_ctx* c, const int32_t* from_lo, const int32_t* from_hi) {
+  int rc = strip_check(c);
+  if (rc) return rc;
+  // the lower neighbour's hi-halo covers our first rows; the upper neighbour's lo-halo our last rows
+  for (int side = 0; side < 2; side++) {
+    const int rows = side == 0 ? c->halo_lo : c->halo_hi;  // symmetric halos: neighbour keeps as many rows of us
+    const int32_t* in = side == 0 ? from_lo : from_hi;
+    if (!rows || !in) continue;
+    const size_t n = (size_t)rows * c->size;
+    const size_t off = side == 0 ? (size_t)(c->m.row0 - c->m.xlo) * c->size : (size_t)(c->m.row1 - rows - c->m.xlo) * c->size;
+    strip_add_rows_kernel<<<grid_for(c, n), 256, 0, c->stream>>>(c->m.h[0] + off, c->m.h[1] + off, in, n);
+    c->launches++;
+  }
+  CU(cudaGetLastError());
+  return SHX_OK;
+}
+
+int shx_strip_pack_boundary(shx_ctx* c, int32_t* dev_lo, int32_t* dev_hi) {
+  int rc = strip_check(c);
+  if (rc) return rc;
+  for (int side = 0; side < 2; side++) {
+    const int rows = side == 0 ? c->halo_lo : c->halo_hi;
+    int32_t* out = side == 0 ? dev_lo : dev_hi;
+    if (!rows || !out) continue;
+    const size_t n = (size_t)rows * c->size;
+    const size_t off = side == 0 ? (size_t)(c->m.row0 - c->m.xlo) * c->size : (size_t)(c->m.row1 - rows - c->m.xlo) * c->size;
+    CU(cudaMemcpyAsync(out, c->m.h[0] + off, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
+  }
+  return SHX_OK;
+}
+
+int shx_strip_set_halo(shx_ctx* c, const int32_t* dev_lo, const int32_t* dev_hi) {
+  int rc = strip_check(c);
+  if (rc) return rc;
+  for (int side = 0; side < 2; side++) {
+    const int rows = side == 0 ? c->halo_lo : c->halo_hi;
+    const int32_t* in = side == 0 ? dev_lo : dev_hi;
+    if (!rows || !in) continue;
+    const size_t n = (size_t)rows * c->size;
+    const size_t off = side == 0 ? 0 : (size_t)(c->m.row1 - c->m.xlo) * c->size;
+    strip_copy_rows_kernel<<<grid_for(c, n), 256, 0, c->stream>>>(c->m.h[0] + off, c->m.h[1] + off, c->d_halo_ref[side], in, n);
+    c->launches++;
+  }
+  CU(cudaGetLastError());
+  return SHX_OK;
+}
+
+int shx_strip_pack_migrants(shx_ctx* c, shx_drop* dev_lo, shx_drop* dev_hi, size_t cap, int* n_lo, int* n_hi) {
+  int rc = strip_check(c);
+  if (rc) return rc;
+  if (!dev_lo || !dev_hi || !n_lo || !n_hi) return fail(SHX_ERR_ARG, "null argument");
+  CU(cudaMemsetAsync(c->d_u32 + 2, 0, 2 * sizeof(unsigned), c->stream));
+  strip_pack_migrants_kernel<<<grid_for(c, c->last_n), 256, 0, c->stream>>>(c->d_drops, (unsigned)c->last_n, dev_lo, dev_hi,
+                                                                               (unsigned)cap, c->d_u32 + 2);
+  c->launches++;
+  CU(cudaGetLastError());
+  unsigned counts[2];
+  CU(cudaMemcpyAsync(counts, c->d_u32 + 2, sizeof counts, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (counts[0] > cap || counts[1] > cap) return fail(SHX_ERR_CAPACITY, "migrant outbox too small");
+  *n_lo = (int)counts[0];
+  *n_hi = (int)counts[1];
+  return SHX_OK;
+}
+
+int shx_strip_run_device_drops(shx_ctx* c, const shx_drop* dev_drops, size_t n, shx_stats* out) {
+  int rc = strip_check(c);
+  if (rc) return rc;
+  if (n > c->max_drops) return fail(SHX_ERR_CAPACITY, "more drops than max_drops");
+  if ((rc = begin_call(c))) return rc;
+  if (n) CU(cudaMemcpyAsync(c->d_drops, dev_drops, n * sizeof(shx_drop), cudaMemcpyDeviceToDevice, c->stream));
+  if ((rc = run_device_drops(c, n, false))) return rc;
+  if (out) return fetch_stats(c, out);
+  return SHX_OK;
+}
+
+}  // extern "C"
