@@ -90,8 +90,11 @@ typedef struct {
   uint64_t launches; /* kernels launched by this call */
 } shx_stats;
 
-#define SHX_HEIGHT_FRAC_BITS 26
-#define SHX_TRACK_FRAC_BITS 32
+#define SHX_HEIGHT_FRAC_BITS 26 /* heights: Q5.26 in an int32, |h| < 31 */
+#define SHX_TRACK_FRAC_BITS 20  /* discharge/momentum tracks: Q11.20 in an int32; a call that pushes a
+                                   discharge track past 1024 (about 1024 drop visits of ONE cell) fails
+                                   with SHX_ERR_RANGE instead of wrapping */
+#define SHX_LEDGER_FRAC_BITS 32 /* fx_sed_* sums: Q31.32 in an int64 */
 
 enum {
   SHX_MODE_BATCHED = 0,   /* all drops of a call advance in lock step; integer atomics; deterministic */
@@ -107,6 +110,10 @@ typedef struct {
   size_t max_drops;    /* capacity of the drop buffers; 0 = maparea*1024 */
   int block_threads;   /* 0 = choose; descend kernel CTA size */
   int grid_blocks;     /* 0 = choose; descend kernel grid */
+  int variant;         /* 0 = 64-register build (1024 threads/SM), 1 = 128-register build (512 threads/SM) */
+  int keep_tracks;     /* 0: erode's EMA pass also zeroes the *_track accumulators (the reset the reference
+                          does at the START of the next call, world.h:56-61, hoisted into the same pass);
+                          1: leave them readable after erode, at the cost of one more pass per call */
 } shx_config;
 
 typedef struct shx_ctx shx_ctx;
@@ -163,10 +170,12 @@ int shx_add_rootdensity(shx_ctx* c, const int* xy, const float* delta, size_t n)
 /* device-side seeded synthetic terrain (value-noise fBm normalised to [0,1]); other fields zeroed */
 int shx_synth_terrain(shx_ctx* c, uint32_t seed);
 
-/* raw device state, planar x*size+y over the stored rows (tests: bit-exact comparison with the
- * lock-step oracle).  Any pointer may be NULL.  hq: Q5.26 planes; field4: discharge, momentumx,
- * momentumy, rootdensity; track4: Q31.32 discharge, momentumx, momentumy, pad. */
-int shx_download_raw(shx_ctx* c, int32_t* hq0, int32_t* hq1, float* field4, int64_t* track4);
+/* raw device state over the stored rows, cell index (x-xlo)*size+y (tests: bit-exact comparison
+ * with the lock-step oracle).  Either pointer may be NULL.
+ *   hq2:   2 int32 per cell, the two Q5.26 height planes interleaved
+ *   rec32: 32 bytes per cell {f32 discharge, momentumx, momentumy, rootdensity,
+ *                             i32 Q11.20 discharge_track, momentumx_track, momentumy_track, pad} */
+int shx_download_raw(shx_ctx* c, int32_t* hq2, void* rec32);
 int shx_stored_rows(const shx_ctx* c, int* xlo, int* nrows);
 
 /* ---- row-strip exchange (multi-GPU): buffers are DEVICE pointers owned by the caller

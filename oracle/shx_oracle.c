@@ -13,9 +13,14 @@
 #include <stdlib.h>
 #include <string.h>
 
-#define TSCALE 4294967296.0 /* 2^32 */
-static int64_t tq(float v) { return (int64_t)llrint((double)v * TSCALE); }
-static int64_t tqd(double v) { return (int64_t)llrint(v * TSCALE); }
+/* sediment ledger: Q31.32 (power-of-two scaling is exact in fp32) */
+static int64_t tq(float v) { return (int64_t)llrintf(v * 4294967296.0f); }
+/* track accumulators: Q11.20 in an int32 */
+#define TRACK_SCALE 1048576.0f
+#define TRACK_INV 9.5367431640625e-7f
+static int32_t trq(float v) { return (int32_t)lrintf(v * TRACK_SCALE); }
+static float track_f(int32_t v) { return (float)v * TRACK_INV; }
+static int32_t wrap_add(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
 
 /* ------------------------------------------------------------------ params */
 
@@ -277,7 +282,7 @@ int orc_seq_descend(orc_seq_world* w, orc_drop* d, orc_stats* st) { /* water.h:5
   const float carried = d->sediment;
   d->sediment = (float)((double)d->sediment / (1.0 - (double)P->evapRate)); /* :135 */
   d->volume = (float)((double)d->volume * (1.0 - (double)P->evapRate));     /* :136 */
-  if (st) st->fx_sed_inflation += tqd((double)d->sediment - (double)carried);
+  if (st) st->fx_sed_inflation += tq(d->sediment) - tq(carried);
   (void)before;
 
   if (out) { /* :139-142 */
@@ -375,14 +380,13 @@ void orc_ls_upload(orc_ls_world* w, const orc_cell* tiled) {
       w->field[4 * i + 1] = c->momentumx;
       w->field[4 * i + 2] = c->momentumy;
       w->field[4 * i + 3] = c->rootdensity;
-      w->track[i].discharge = tq(c->discharge_track);
-      w->track[i].momentumx = tq(c->momentumx_track);
-      w->track[i].momentumy = tq(c->momentumy_track);
+      w->track[i].discharge = trq(c->discharge_track);
+      w->track[i].momentumx = trq(c->momentumx_track);
+      w->track[i].momentumy = trq(c->momentumy_track);
       w->track[i].pad = 0;
     }
 }
 
-static float track_f(int64_t v) { return (float)((double)v * (1.0 / TSCALE)); }
 
 void orc_ls_download(const orc_ls_world* w, orc_cell* tiled) {
   for (int x = 0; x < w->size; x++)
@@ -552,9 +556,9 @@ static int ls_step(orc_ls_world* w, const int32_t* R, orc_drop* d, int32_t* D, i
   d->px += d->sx; /* :111 */
   d->py += d->sy;
 
-  w->track[ci].discharge += tq(d->volume); /* :115-117 */
-  w->track[ci].momentumx += tq(d->volume * d->sx);
-  w->track[ci].momentumy += tq(d->volume * d->sy);
+  w->track[ci].discharge = wrap_add(w->track[ci].discharge, trq(d->volume)); /* :115-117 */
+  w->track[ci].momentumx = wrap_add(w->track[ci].momentumx, trq(d->volume * d->sx));
+  w->track[ci].momentumy = wrap_add(w->track[ci].momentumy, trq(d->volume * d->sy));
 
   const int nix = trunc_i(d->px), niy = trunc_i(d->py);
   const int out = ls_oob(w, nix, niy);
@@ -578,7 +582,7 @@ static int ls_step(orc_ls_world* w, const int32_t* R, orc_drop* d, int32_t* D, i
   const float carried = d->sediment;
   d->sediment = (float)((double)d->sediment / (1.0 - (double)P->evapRate)); /* :135 */
   d->volume = (float)((double)d->volume * (1.0 - (double)P->evapRate));     /* :136 */
-  st->fx_sed_inflation += tqd((double)d->sediment - (double)carried);
+  st->fx_sed_inflation += tq(d->sediment) - tq(carried);
   if (out) { /* :139-142 */
     st->term_oob++;
     st->fx_sed_oob_lost += tq(d->sediment);
@@ -645,7 +649,10 @@ void orc_ls_reset_tracks(orc_ls_world* w) { /* world.h:56-61 */
   memset(w->track, 0, sizeof(orc_track) * (size_t)w->size * w->size);
 }
 
-void orc_ls_ema(orc_ls_world* w) { /* world.h:81-86 */
+/* world.h:81-86; returns 1 if a discharge accumulator left the Q11.20 range (the product then
+ * reports SHX_ERR_RANGE).  reset != 0 also zeroes the tracks (world.h:56-61 of the next call). */
+int orc_ls_ema(orc_ls_world* w, int reset) {
+  int overflow = 0;
   const size_t n = (size_t)w->size * w->size;
   const float lr = w->p.lrate;
   for (size_t i = 0; i < n; i++) {
@@ -653,7 +660,10 @@ void orc_ls_ema(orc_ls_world* w) { /* world.h:81-86 */
     f[0] = (1.0f - lr) * f[0] + lr * track_f(w->track[i].discharge);
     f[1] = (1.0f - lr) * f[1] + lr * track_f(w->track[i].momentumx);
     f[2] = (1.0f - lr) * f[2] + lr * track_f(w->track[i].momentumy);
+    if (w->track[i].discharge < 0 || w->track[i].discharge > (1 << 30)) overflow = 1;
+    if (reset) w->track[i].discharge = w->track[i].momentumx = w->track[i].momentumy = 0;
   }
+  return overflow;
 }
 
 void orc_ls_erode_spawnlist(orc_ls_world* w, const float* xy, size_t n, orc_stats* st) {
@@ -661,7 +671,7 @@ void orc_ls_erode_spawnlist(orc_ls_world* w, const float* xy, size_t n, orc_stat
   orc_ls_reset_tracks(w);
   orc_ls_make_drops(w, xy, n, drops, st);
   orc_ls_run(w, drops, n, st, NULL, 0, NULL);
-  orc_ls_ema(w);
+  orc_ls_ema(w, 1);
   free(drops);
 }
 

@@ -79,7 +79,8 @@ typedef struct {
 } orc_stats;
 
 #define ORC_HEIGHT_FRAC_BITS 26
-#define ORC_TRACK_FRAC_BITS 32
+#define ORC_TRACK_FRAC_BITS 20
+#define ORC_LEDGER_FRAC_BITS 32
 
 void orc_default_params(orc_params* p, int mapsize);
 
@@ -111,7 +112,7 @@ int orc_seq_trace_drop(orc_seq_world* w, float x, float y, float* trace, int max
 
 /* ---- lock-step fixed-point semantics on planar row-major planes */
 typedef struct {
-  int64_t discharge, momentumx, momentumy, pad;
+  int32_t discharge, momentumx, momentumy, pad;
 } orc_track;
 
 typedef struct {
@@ -119,7 +120,7 @@ typedef struct {
   int size;         /* cells per side = mapsize*tilesize */
   int32_t* h[2];    /* height planes, Q5.26, index x*size+y; equal outside a batch */
   float* field;     /* 4 floats per cell: discharge, momentumx, momentumy, rootdensity */
-  orc_track* track; /* Q31.32 accumulators */
+  orc_track* track; /* Q11.20 accumulators */
   int row0, row1;   /* rows [row0,row1) are owned (strip); 0,size for the whole map */
 } orc_ls_world;
 
@@ -135,7 +136,7 @@ void orc_ls_make_drops(const orc_ls_world* w, const float* xy, size_t n, orc_dro
 /* march all drops to completion, one step per phase */
 void orc_ls_run(orc_ls_world* w, orc_drop* drops, size_t n, orc_stats* st, float* trace0, int trace_cap, int* trace_n);
 void orc_ls_reset_tracks(orc_ls_world* w); /* world.h:56-61 */
-void orc_ls_ema(orc_ls_world* w);          /* world.h:81-86 */
+int orc_ls_ema(orc_ls_world* w, int reset); /* world.h:81-86 (+ :56-61 when reset); 1 = track overflow */
 /* == erode(cycles): reset tracks, spawn, run, EMA */
 void orc_ls_erode(orc_ls_world* w, int cycles, uint64_t seed, uint64_t epoch, orc_stats* st);
 void orc_ls_erode_spawnlist(orc_ls_world* w, const float* xy, size_t n, orc_stats* st);

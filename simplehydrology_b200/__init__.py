@@ -26,7 +26,7 @@ MODE_BATCHED, MODE_SEQUENTIAL = 0, 1
 F_HEIGHT, F_DISCHARGE, F_MOMENTUM, F_TRACKS, F_ROOTDENSITY, F_ALL = 1, 2, 4, 8, 16, 31
 DROP_ALIVE, DROP_CASCADE, DROP_DONE_AGE, DROP_DONE_VOL, DROP_DONE_OOB = 1, 2, 4, 8, 16
 DROP_REJECTED, DROP_DONE_NULL, DROP_MIGRATE_LO, DROP_MIGRATE_HI = 32, 64, 128, 256
-HEIGHT_FRAC_BITS, TRACK_FRAC_BITS = 26, 32
+HEIGHT_FRAC_BITS, TRACK_FRAC_BITS, LEDGER_FRAC_BITS = 26, 20, 32
 
 
 class ShxError(RuntimeError):
@@ -44,7 +44,8 @@ class Params(C.Structure):
 
 class Config(C.Structure):
     _fields_ = [("device", C.c_int), ("mode", C.c_int), ("row0", C.c_int), ("row1", C.c_int), ("halo", C.c_int),
-                ("max_drops", C.c_size_t), ("block_threads", C.c_int), ("grid_blocks", C.c_int)]
+                ("max_drops", C.c_size_t), ("block_threads", C.c_int), ("grid_blocks", C.c_int), ("variant", C.c_int),
+                ("keep_tracks", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -99,7 +100,7 @@ def lib():
     L.shx_run_drops.argtypes = [vp, vp, sz, C.POINTER(Stats)]
     L.shx_add_rootdensity.argtypes = [vp, vp, vp, sz]
     L.shx_synth_terrain.argtypes = [vp, C.c_uint32]
-    L.shx_download_raw.argtypes = [vp, vp, vp, vp, vp]
+    L.shx_download_raw.argtypes = [vp, vp, vp]
     L.shx_stored_rows.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.shx_strip_pack_halo_delta.argtypes = [vp, vp, vp]
     L.shx_strip_apply_halo_delta.argtypes = [vp, vp, vp]
@@ -125,13 +126,14 @@ class World:
     """Device-resident world; `erode(cycles)` is the reference's World::erode (world.h:54-88)."""
 
     def __init__(self, params=None, mapsize=1, mode=MODE_BATCHED, device=0, row0=0, row1=0, halo=2, max_drops=0,
-                 block_threads=0, grid_blocks=0):
+                 block_threads=0, grid_blocks=0, variant=0, keep_tracks=0):
         self.L = lib()
         self.params = params if params is not None else default_params(mapsize)
         cfg = Config()
         self.L.shx_default_config(C.byref(cfg))
         cfg.device, cfg.mode, cfg.row0, cfg.row1, cfg.halo = device, mode, row0, row1, halo
-        cfg.max_drops, cfg.block_threads, cfg.grid_blocks = max_drops, block_threads, grid_blocks
+        cfg.max_drops, cfg.block_threads, cfg.grid_blocks, cfg.variant = max_drops, block_threads, grid_blocks, variant
+        cfg.keep_tracks = keep_tracks
         self.cfg = cfg
         self.size = self.params.mapsize * self.params.tilesize
         self.ncells = self.size * self.size
@@ -189,15 +191,17 @@ class World:
         self._check(fn(self._h, out.ctypes.data, out.size, mask))
         return out
 
-    def download_raw(self, planes=True, field=True, track=True):
+    def download_raw(self):
+        """(plane0, plane1, field[...,4] f32, track[...,4] i32) over the stored rows -- the device's own
+        fixed-point state, for bit-exact comparison with the lock-step oracle"""
         _, nrows = self.stored_rows()
         shape = (nrows, self.size)
-        h0 = np.zeros(shape, np.int32) if planes else None
-        h1 = np.zeros(shape, np.int32) if planes else None
-        f = np.zeros(shape + (4,), np.float32) if field else None
-        t = np.zeros(shape + (4,), np.int64) if track else None
-        self._check(self.L.shx_download_raw(self._h, _ptr(h0), _ptr(h1), _ptr(f), _ptr(t)))
-        return h0, h1, f, t
+        hq = np.zeros(shape + (2,), np.int32)
+        rec = np.zeros(shape + (8,), np.int32)
+        self._check(self.L.shx_download_raw(self._h, hq.ctypes.data, rec.ctypes.data))
+        field = np.ascontiguousarray(rec[..., :4]).view(np.float32)
+        track = np.ascontiguousarray(rec[..., 4:])
+        return np.ascontiguousarray(hq[..., 0]), np.ascontiguousarray(hq[..., 1]), field, track
 
     def synth_terrain(self, seed):
         self._check(self.L.shx_synth_terrain(self._h, seed))

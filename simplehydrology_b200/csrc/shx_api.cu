@@ -1,6 +1,7 @@
 // shx C ABI (include/shx.h): context, transfers and kernel launches.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false -prec-div=true -prec-sqrt=true
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -52,9 +53,11 @@ struct shx_ctx {
   int sm_count = 0;
   uint64_t epoch = 0;
   uint64_t launches = 0;
-  size_t last_n = 0;         // drops of the last run still sitting in d_drops
-  int cap_blocks_big = 0;    // co-resident CTAs of the 64-register instantiation at block_big
+  size_t last_n = 0;        // drops of the last run still sitting in d_drops
+  bool tracks_clean = true; // all track accumulators are zero (world.h:56-61 already satisfied)
+  int cap_blocks_big = 0;   // co-resident CTAs of the multi-CTA instantiation at block_big
   int block_big = 256;
+  const void* kernel_big = nullptr;
 };
 
 static StepParams step_params(const shx_params& p) {
@@ -63,6 +66,10 @@ static StepParams step_params(const shx_params& p) {
   s.entrainment = p.entrainment; s.gravity = p.gravity; s.momentumTransfer = p.momentumTransfer;
   s.maxdiff = p.maxdiff; s.settling = p.settling; s.lod = (float)p.lodsize; s.mapscale = (float)p.mapscale;
   s.lrate = p.lrate;
+  // world.h:123,145: length(vec2(nn)) * maxdiff * lodsize, fp32 left to right
+  s.lim_axis = 1.0f * p.maxdiff * (float)p.lodsize;
+  s.lim_diag = sqrtf(2.0f) * p.maxdiff * (float)p.lodsize;
+  s.keep = 1.0 - (double)p.evapRate;  // water.h:135-136
   return s;
 }
 
@@ -74,10 +81,19 @@ static int grid_for(const shx_ctx* c, size_t n, int block = 256) {
   return (int)std::max<size_t>(1, std::min(want, cap));
 }
 
-// the two instantiations: one CTA of up to 1024 threads (small batches: the barrier is a plain
-// __syncthreads) and the occupancy-oriented one (<= 64 registers, 1024 threads per SM)
+static size_t descend_smem(int block) { return (size_t)(9 + 16) * sizeof(int32_t) * block; }
+
+// Instantiations {max CTA threads, min CTAs/SM}.  KERNEL_SMALL: one CTA of up to 1024 threads for
+// small batches (the barrier is a plain __syncthreads).  Multi-CTA: the first four cap registers at
+// 64 (1024 threads per SM); variant 1 allows 128 registers (512 threads per SM).
 #define KERNEL_SMALL descend_lockstep_kernel<1024, 1>
-#define KERNEL_BIG descend_lockstep_kernel<256, 4>
+static const void* big_kernel(int block, int variant) {
+  if (variant == 1) return block <= 256 ? (const void*)descend_lockstep_kernel<256, 2> : (const void*)descend_lockstep_kernel<512, 1>;
+  if (block <= 128) return (const void*)descend_lockstep_kernel<128, 8>;
+  if (block <= 256) return (const void*)descend_lockstep_kernel<256, 4>;
+  if (block <= 512) return (const void*)descend_lockstep_kernel<512, 2>;
+  return (const void*)KERNEL_SMALL;
+}
 
 extern "C" {
 
@@ -112,7 +128,7 @@ void shx_default_config(shx_config* c) {
 void shx_destroy(shx_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->cfg.device);
-  cudaFree(c->m.h[0]); cudaFree(c->m.h[1]); cudaFree(c->m.field); cudaFree(c->m.track);
+  cudaFree(c->m.hq); cudaFree(c->m.rec);
   cudaFree(c->d_drops); cudaFree(c->d_xy); cudaFree(c->d_bar); cudaFree(c->d_stats); cudaFree(c->d_flags);
   cudaFree(c->d_trace); cudaFree(c->d_u32); cudaFree(c->d_halo_ref[0]); cudaFree(c->d_halo_ref[1]);
   cudaFree(c->d_stage);
@@ -125,8 +141,8 @@ int shx_create(shx_ctx** out, const shx_params* p, const shx_config* cfg_in) {
   if (!out || !p) return fail(SHX_ERR_ARG, "shx_create: null argument");
   *out = nullptr;
   if (p->lodsize != 1) return fail(SHX_ERR_ARG, "only lodsize == 1 is supported (cellpool.h:178)");
-  if (p->mapsize < 1 || p->tilesize < 4 || (long long)p->mapsize * p->tilesize > 46340)
-    return fail(SHX_ERR_ARG, "bad geometry");
+  if (p->mapsize < 1 || p->tilesize < 4 || (long long)p->mapsize * p->tilesize > 32768)
+    return fail(SHX_ERR_ARG, "bad geometry (side must be <= 32768 cells)");
   shx_config cfg;
   if (cfg_in) cfg = *cfg_in; else shx_default_config(&cfg);
   const int size = p->mapsize * p->tilesize;
@@ -170,10 +186,8 @@ int shx_create(shx_ctx** out, const shx_params* p, const shx_config* cfg_in) {
       return fail(SHX_ERR_NOMEM, "cudaMalloc failed for " #ptr);           \
     }                                                                      \
   } while (0)
-  ALLOC(c->m.h[0], c->stored_cells * sizeof(int32_t));
-  ALLOC(c->m.h[1], c->stored_cells * sizeof(int32_t));
-  ALLOC(c->m.field, c->stored_cells * sizeof(float4));
-  ALLOC(c->m.track, c->stored_cells * sizeof(Track));
+  ALLOC(c->m.hq, c->stored_cells * sizeof(int2));
+  ALLOC(c->m.rec, c->stored_cells * sizeof(CellRec));
   ALLOC(c->d_drops, c->max_drops * sizeof(shx_drop));
   ALLOC(c->d_xy, c->max_drops * 2 * sizeof(float));
   ALLOC(c->d_bar, sizeof(GridBar));
@@ -192,16 +206,18 @@ int shx_create(shx_ctx** out, const shx_params* p, const shx_config* cfg_in) {
     shx_destroy(c);
     return fail(SHX_ERR_NOMEM, "cudaMallocHost failed");
   }
-  cudaMemset(c->m.h[0], 0, c->stored_cells * sizeof(int32_t));
-  cudaMemset(c->m.h[1], 0, c->stored_cells * sizeof(int32_t));
-  cudaMemset(c->m.field, 0, c->stored_cells * sizeof(float4));
-  cudaMemset(c->m.track, 0, c->stored_cells * sizeof(Track));
+  cudaMemset(c->m.hq, 0, c->stored_cells * sizeof(int2));
+  cudaMemset(c->m.rec, 0, c->stored_cells * sizeof(CellRec));
   cudaMemset(c->d_stats, 0, ST_COUNT * 8);
   cudaMemset(c->d_flags, 0, 4 * sizeof(int));
 
-  c->block_big = cfg.block_threads > 0 ? std::min(256, (cfg.block_threads + 31) / 32 * 32) : 256;
+  c->block_big = cfg.block_threads > 0 ? std::min(1024, (cfg.block_threads + 31) / 32 * 32) : 256;
+  if (cfg.variant == 1) c->block_big = std::min(c->block_big, 512);
+  c->kernel_big = big_kernel(c->block_big, cfg.variant);
   int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, KERNEL_BIG, c->block_big, 9 * sizeof(int32_t) * c->block_big) != cudaSuccess ||
+  if (cudaFuncSetAttribute(KERNEL_SMALL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)descend_smem(1024)) != cudaSuccess ||
+      cudaFuncSetAttribute(c->kernel_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)descend_smem(c->block_big)) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, c->kernel_big, c->block_big, descend_smem(c->block_big)) != cudaSuccess ||
       nb < 1) {
     shx_destroy(c);
     return fail(SHX_ERR_CUDA, "descend kernel does not fit on this device");
@@ -268,8 +284,10 @@ static int refresh_halo_ref(shx_ctx* c) {
     if (!rows || !c->d_halo_ref[side]) continue;
     const size_t n = (size_t)rows * c->size;
     const size_t off = side == 0 ? 0 : (size_t)(c->m.row1 - c->m.xlo) * c->size;
-    CU(cudaMemcpyAsync(c->d_halo_ref[side], c->m.h[0] + off, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
+    strip_get_rows_kernel<<<grid_for(c, n), 256, 0, c->stream>>>(c->m.hq + off, c->d_halo_ref[side], n);
+    c->launches++;
   }
+  CU(cudaGetLastError());
   return SHX_OK;
 }
 
@@ -291,11 +309,13 @@ int shx_upload(shx_ctx* c, const shx_cell* pool, size_t ncells) {
     }
   }
   CU(cudaGetLastError());
+  c->tracks_clean = false;  // the host's track values were taken over as they are
   int rc = refresh_halo_ref(c);
   if (rc) return rc;
   CU(cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  if (c->h_flags[0]) return fail(SHX_ERR_RANGE, "a height is outside (-31, 31): does not fit Q5.26");
+  if (c->h_flags[0])
+    return fail(SHX_ERR_RANGE, "a height is outside (-31, 31) or a track outside (-1024, 1024): does not fit the fixed point");
   return SHX_OK;
 }
 
@@ -308,9 +328,9 @@ int shx_download_async(shx_ctx* c, shx_cell* pool, size_t ncells, unsigned mask)
   const int ts = c->p.tilesize, ms = c->p.mapsize;
   const size_t tile_cells = (size_t)ts * ts;
   // byte runs of the 32-byte record selected by the mask
-  bool want[8] = {(mask & SHX_F_HEIGHT) != 0, (mask & SHX_F_DISCHARGE) != 0, (mask & SHX_F_MOMENTUM) != 0,
-                  (mask & SHX_F_MOMENTUM) != 0, (mask & SHX_F_TRACKS) != 0, (mask & SHX_F_TRACKS) != 0,
-                  (mask & SHX_F_TRACKS) != 0, (mask & SHX_F_ROOTDENSITY) != 0};
+  const bool want[8] = {(mask & SHX_F_HEIGHT) != 0, (mask & SHX_F_DISCHARGE) != 0, (mask & SHX_F_MOMENTUM) != 0,
+                        (mask & SHX_F_MOMENTUM) != 0, (mask & SHX_F_TRACKS) != 0, (mask & SHX_F_TRACKS) != 0,
+                        (mask & SHX_F_TRACKS) != 0, (mask & SHX_F_ROOTDENSITY) != 0};
   for (int ti = 0; ti < ms; ti++) {
     const int lx0 = std::max(c->m.row0 - ti * ts, 0), lx1 = std::min(c->m.row1 - ti * ts, ts);
     if (lx0 >= lx1) continue;
@@ -347,14 +367,12 @@ int shx_download(shx_ctx* c, shx_cell* pool, size_t ncells, unsigned mask) {
   return SHX_OK;
 }
 
-int shx_download_raw(shx_ctx* c, int32_t* hq0, int32_t* hq1, float* field4, int64_t* track4) {
+int shx_download_raw(shx_ctx* c, int32_t* hq2, void* rec32) {
   if (!c) return fail(SHX_ERR_ARG, "null context");
   CU(cudaSetDevice(c->cfg.device));
   CU(cudaStreamSynchronize(c->stream));
-  if (hq0) CU(cudaMemcpy(hq0, c->m.h[0], c->stored_cells * sizeof(int32_t), cudaMemcpyDeviceToHost));
-  if (hq1) CU(cudaMemcpy(hq1, c->m.h[1], c->stored_cells * sizeof(int32_t), cudaMemcpyDeviceToHost));
-  if (field4) CU(cudaMemcpy(field4, c->m.field, c->stored_cells * sizeof(float4), cudaMemcpyDeviceToHost));
-  if (track4) CU(cudaMemcpy(track4, c->m.track, c->stored_cells * sizeof(Track), cudaMemcpyDeviceToHost));
+  if (hq2) CU(cudaMemcpy(hq2, c->m.hq, c->stored_cells * sizeof(int2), cudaMemcpyDeviceToHost));
+  if (rec32) CU(cudaMemcpy(rec32, c->m.rec, c->stored_cells * sizeof(CellRec), cudaMemcpyDeviceToHost));
   return SHX_OK;
 }
 
@@ -362,10 +380,15 @@ int shx_download_raw(shx_ctx* c, int32_t* hq0, int32_t* hq1, float* field4, int6
 
 static int fetch_stats(shx_ctx* c, shx_stats* out) {
   CU(cudaMemcpyAsync(c->h_stats, c->d_stats, ST_COUNT * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   if (out) {
     memcpy(out, c->h_stats, sizeof(shx_stats));
     out->launches = c->launches;
+  }
+  if (c->h_flags[0]) {
+    CU(cudaMemsetAsync(c->d_flags, 0, sizeof(int), c->stream));
+    return fail(SHX_ERR_RANGE, "a discharge track left the Q11.20 range (more than ~1024 drop visits of one cell in one call)");
   }
   return SHX_OK;
 }
@@ -380,23 +403,29 @@ static int begin_call(shx_ctx* c) {
 int shx_reset_tracks(shx_ctx* c) {  // world.h:56-61
   if (!c) return fail(SHX_ERR_ARG, "null context");
   CU(cudaSetDevice(c->cfg.device));
-  CU(cudaMemsetAsync(c->m.track, 0, c->stored_cells * sizeof(Track), c->stream));
+  const int grid = (int)std::min<size_t>((c->stored_cells + 255) / 256, (size_t)c->sm_count * 16);
+  reset_tracks_kernel<<<grid, 256, 0, c->stream>>>(c->m.rec, c->stored_cells);
+  c->launches++;
+  c->tracks_clean = true;
+  CU(cudaGetLastError());
   return SHX_OK;
 }
 
-int shx_ema(shx_ctx* c) {  // world.h:81-86
-  if (!c) return fail(SHX_ERR_ARG, "null context");
-  CU(cudaSetDevice(c->cfg.device));
+static int ema_launch(shx_ctx* c, bool reset) {  // world.h:81-86 (+ :56-61 for the next call)
   const size_t off = (size_t)(c->m.row0 - c->m.xlo) * c->size;
   const int grid = (int)std::min<size_t>((c->owned_cells + 255) / 256, (size_t)c->sm_count * 16);
-  if (sequential(c))
-    ema_sequential_kernel<<<grid, 256, 0, c->stream>>>(c->m.field + off, reinterpret_cast<const float4*>(c->m.track + off),
-                                                        c->owned_cells, c->p.lrate);
-  else
-    ema_kernel<<<grid, 256, 0, c->stream>>>(c->m.field + off, c->m.track + off, c->owned_cells, c->p.lrate);
+  ema_kernel<<<grid, 256, 0, c->stream>>>(c->m.rec + off, c->owned_cells, c->p.lrate, sequential(c) ? 1 : 0, reset ? 1 : 0,
+                                           c->d_flags);
   c->launches++;
+  c->tracks_clean = reset;
   CU(cudaGetLastError());
   return SHX_OK;
+}
+
+int shx_ema(shx_ctx* c) {
+  if (!c) return fail(SHX_ERR_ARG, "null context");
+  CU(cudaSetDevice(c->cfg.device));
+  return ema_launch(c, false);
 }
 
 // march n drops already in c->d_drops
@@ -404,12 +433,10 @@ static int run_device_drops(shx_ctx* c, size_t n, bool trace) {
   c->last_n = n;
   if (n == 0) return SHX_OK;
   if (n > c->max_drops) return fail(SHX_ERR_CAPACITY, "more drops than max_drops");
+  c->tracks_clean = false;
   if (sequential(c)) {
     SequentialArgs a;
-    a.h = reinterpret_cast<float*>(c->m.h[0]);
-    a.field = c->m.field;
-    a.trackf = reinterpret_cast<float4*>(c->m.track);
-    a.size = c->size;
+    a.m = c->m;
     a.P = step_params(c->p);
     a.drops = c->d_drops;
     a.ndrops = (unsigned)n;
@@ -438,20 +465,20 @@ static int run_device_drops(shx_ctx* c, size_t n, bool trace) {
     CU(cudaMemsetAsync(c->d_bar, 0, sizeof(GridBar), c->stream));
     void* args[] = {&a};
     size_t take;
-    const bool force_grid = c->cfg.grid_blocks > 0;
+    const bool force_grid = c->cfg.grid_blocks > 0 || c->cfg.block_threads > 0;
     if (left <= 1024 && !force_grid) {
       take = left;
       a.ndrops = (unsigned)take;
       const int block = (int)((take + 31) / 32 * 32);
-      CU(cudaLaunchCooperativeKernel((void*)KERNEL_SMALL, dim3(1), dim3(block), args, 9 * sizeof(int32_t) * block, c->stream));
+      CU(cudaLaunchCooperativeKernel((void*)KERNEL_SMALL, dim3(1), dim3(block), args, descend_smem(block), c->stream));
     } else {
       const int block = c->block_big;
       int cap = c->cap_blocks_big;
-      if (force_grid) cap = std::min(cap, c->cfg.grid_blocks);
+      if (c->cfg.grid_blocks > 0) cap = std::min(cap, c->cfg.grid_blocks);
       take = std::min(left, (size_t)cap * block);
       a.ndrops = (unsigned)take;
       const int grid = (int)((take + block - 1) / block);
-      CU(cudaLaunchCooperativeKernel((void*)KERNEL_BIG, dim3(grid), dim3(block), args, 9 * sizeof(int32_t) * block, c->stream));
+      CU(cudaLaunchCooperativeKernel(c->kernel_big, dim3(grid), dim3(block), args, descend_smem(block), c->stream));
     }
     c->launches++;
     done += take;
@@ -469,15 +496,15 @@ static int spawn_device(shx_ctx* c, int cycles, uint64_t seed, uint64_t epoch, s
   *n_out = n;
   if (!n) return SHX_OK;
   SpawnArgs a;
-  a.hq = sequential(c) ? nullptr : c->m.h[0];
-  a.hf = sequential(c) ? reinterpret_cast<const float*>(c->m.h[0]) : nullptr;
-  a.size = c->size; a.xlo = c->m.xlo; a.tilesize = ts; a.mapsize = ms;
+  a.m = c->m;
+  a.sequential = sequential(c) ? 1 : 0;
+  a.tilesize = ts; a.mapsize = ms;
   a.node0 = node0; a.nnodes = nnodes; a.cycles = cycles;
   a.key = mix64(mix64(seed) + epoch);
   a.drops = c->d_drops;
   a.xy = c->d_xy;
   a.stats = c->d_stats;
-  spawn_kernel<<<grid_for(c, n), 256, 0, c->stream>>>(a, c->m.row0, c->m.row1);
+  spawn_kernel<<<grid_for(c, n), 256, 0, c->stream>>>(a);
   c->launches++;
   CU(cudaGetLastError());
   return SHX_OK;
@@ -487,12 +514,12 @@ int shx_erode_async(shx_ctx* c, int cycles, uint64_t seed) {
   if (!c) return fail(SHX_ERR_ARG, "null context");
   int rc = begin_call(c);
   if (rc) return rc;
-  if ((rc = shx_reset_tracks(c))) return rc;  // world.h:56-61
+  if (!c->tracks_clean && (rc = shx_reset_tracks(c))) return rc;  // world.h:56-61
   size_t n = 0;
   if ((rc = spawn_device(c, cycles, seed, c->epoch, &n))) return rc;  // world.h:64-74
   c->epoch++;
   if ((rc = run_device_drops(c, n, false))) return rc;  // world.h:76
-  return shx_ema(c);                                    // world.h:81-86
+  return ema_launch(c, !c->cfg.keep_tracks);            // world.h:81-86
 }
 
 int shx_read_stats(shx_ctx* c, shx_stats* out) {
@@ -511,10 +538,7 @@ static int make_drops_from_xy(shx_ctx* c, const float* xy_host, size_t n) {
   if (n > c->max_drops) return fail(SHX_ERR_CAPACITY, "more drops than max_drops");
   if (!n) return SHX_OK;
   CU(cudaMemcpyAsync(c->d_xy, xy_host, n * 2 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  make_drops_kernel<<<grid_for(c, n), 256, 0, c->stream>>>(
-      c->d_xy, (unsigned)n, sequential(c) ? nullptr : c->m.h[0],
-      sequential(c) ? reinterpret_cast<const float*>(c->m.h[0]) : nullptr, c->size, c->m.xlo, c->m.row0, c->m.row1,
-      c->d_drops, c->d_stats);
+  make_drops_kernel<<<grid_for(c, n), 256, 0, c->stream>>>(c->d_xy, (unsigned)n, c->m, sequential(c) ? 1 : 0, c->d_drops, c->d_stats);
   c->launches++;
   CU(cudaGetLastError());
   return SHX_OK;
@@ -524,10 +548,10 @@ int shx_erode_spawnlist(shx_ctx* c, const float* xy, size_t n, shx_stats* out) {
   if (!c || (!xy && n)) return fail(SHX_ERR_ARG, "null argument");
   int rc = begin_call(c);
   if (rc) return rc;
-  if ((rc = shx_reset_tracks(c))) return rc;
+  if (!c->tracks_clean && (rc = shx_reset_tracks(c))) return rc;
   if ((rc = make_drops_from_xy(c, xy, n))) return rc;
   if ((rc = run_device_drops(c, n, false))) return rc;
-  if ((rc = shx_ema(c))) return rc;
+  if ((rc = ema_launch(c, !c->cfg.keep_tracks))) return rc;
   return fetch_stats(c, out);
 }
 
@@ -535,11 +559,9 @@ int shx_trace_drop(shx_ctx* c, float x, float y, float* trace7, int max_steps, i
   if (!c || !trace7 || !nsteps || max_steps < 1) return fail(SHX_ERR_ARG, "bad argument");
   int rc = begin_call(c);
   if (rc) return rc;
-  const float xy[2] = {x, y};
   CU(cudaMemsetAsync(c->d_flags + 1, 0, sizeof(int), c->stream));
   // no rejection here: Drop(pos) followed by while(descend()) exactly as a caller of the reference would
   const shx_drop d = {x, y, 0.0f, 0.0f, 1.0f, 0.0f, 0, SHX_DROP_ALIVE};
-  (void)xy;
   const int ix = (int)x, iy = (int)y;
   if (!(x > -1.0f) || !(y > -1.0f) || ix >= c->size || iy >= c->size || ix < c->m.row0 || ix >= c->m.row1) {
     *nsteps = 0;  // water.h:62-68: NULL node -> descend returns false immediately
@@ -605,6 +627,7 @@ int shx_synth_terrain(shx_ctx* c, uint32_t seed) {
   synth_minmax_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->size, seed, c->d_u32);
   synth_fill_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->m, sequential(c) ? 1 : 0, seed, c->d_u32);
   c->launches += 2;
+  c->tracks_clean = true;
   CU(cudaGetLastError());
   int rc = refresh_halo_ref(c);
   if (rc) return rc;
@@ -621,6 +644,12 @@ static int strip_check(shx_ctx* c) {
   return SHX_OK;
 }
 
+// offsets (in cells) of the halo band and of the owned edge band on each side of a strip
+static size_t band_halo(const shx_ctx* c, int side) { return side == 0 ? 0 : (size_t)(c->m.row1 - c->m.xlo) * c->size; }
+static size_t band_edge(const shx_ctx* c, int side, int rows) {
+  return side == 0 ? (size_t)(c->m.row0 - c->m.xlo) * c->size : (size_t)(c->m.row1 - rows - c->m.xlo) * c->size;
+}
+
 int shx_strip_pack_halo_delta(shx_ctx* c, int32_t* dev_lo, int32_t* dev_hi) {
   int rc = strip_check(c);
   if (rc) return rc;
@@ -629,8 +658,7 @@ int shx_strip_pack_halo_delta(shx_ctx* c, int32_t* dev_lo, int32_t* dev_hi) {
     int32_t* out = side == 0 ? dev_lo : dev_hi;
     if (!rows || !out) continue;
     const size_t n = (size_t)rows * c->size;
-    const size_t off = side == 0 ? 0 : (size_t)(c->m.row1 - c->m.xlo) * c->size;
-    strip_halo_delta_kernel<<<grid_for(c, n), 256, 0, c->stream>>>(c->m.h[0] + off, c->d_halo_ref[side], out, n);
+    strip_halo_delta_kernel<<<grid_for(c, n), 256, 0, c->stream>>>(c->m.hq + band_halo(c, side), c->d_halo_ref[side], out, n);
     c->launches++;
   }
   CU(cudaGetLastError());
@@ -642,12 +670,11 @@ int shx_strip_apply_halo_delta(shx_ctx* c, const int32_t* from_lo, const int32_t
   if (rc) return rc;
   // the lower neighbour's hi-halo covers our first rows; the upper neighbour's lo-halo our last rows
   for (int side = 0; side < 2; side++) {
-    const int rows = side == 0 ? c->halo_lo : c->halo_hi;  // symmetric halos: neighbour keeps as many rows of us
+    const int rows = side == 0 ? c->halo_lo : c->halo_hi;  // symmetric halos
     const int32_t* in = side == 0 ? from_lo : from_hi;
     if (!rows || !in) continue;
     const size_t n = (size_t)rows * c->size;
-    const size_t off = side == 0 ? (size_t)(c->m.row0 - c->m.xlo) * c->size : (size_t)(c->m.row1 - rows - c->m.xlo) * c->size;
-    strip_add_rows_kernel<<<grid_for(c, n), 256, 0, c->stream>>>(c->m.h[0] + off, c->m.h[1] + off, in, n);
+    strip_add_rows_kernel<<<grid_for(c, n), 256, 0, c->stream>>>(c->m.hq + band_edge(c, side, rows), in, n);
     c->launches++;
   }
   CU(cudaGetLastError());
@@ -662,9 +689,10 @@ int shx_strip_pack_boundary(shx_ctx* c, int32_t* dev_lo, int32_t* dev_hi) {
     int32_t* out = side == 0 ? dev_lo : dev_hi;
     if (!rows || !out) continue;
     const size_t n = (size_t)rows * c->size;
-    const size_t off = side == 0 ? (size_t)(c->m.row0 - c->m.xlo) * c->size : (size_t)(c->m.row1 - rows - c->m.xlo) * c->size;
-    CU(cudaMemcpyAsync(out, c->m.h[0] + off, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
+    strip_get_rows_kernel<<<grid_for(c, n), 256, 0, c->stream>>>(c->m.hq + band_edge(c, side, rows), out, n);
+    c->launches++;
   }
+  CU(cudaGetLastError());
   return SHX_OK;
 }
 
@@ -676,8 +704,7 @@ int shx_strip_set_halo(shx_ctx* c, const int32_t* dev_lo, const int32_t* dev_hi)
     const int32_t* in = side == 0 ? dev_lo : dev_hi;
     if (!rows || !in) continue;
     const size_t n = (size_t)rows * c->size;
-    const size_t off = side == 0 ? 0 : (size_t)(c->m.row1 - c->m.xlo) * c->size;
-    strip_copy_rows_kernel<<<grid_for(c, n), 256, 0, c->stream>>>(c->m.h[0] + off, c->m.h[1] + off, c->d_halo_ref[side], in, n);
+    strip_set_rows_kernel<<<grid_for(c, n), 256, 0, c->stream>>>(c->m.hq + band_halo(c, side), c->d_halo_ref[side], in, n);
     c->launches++;
   }
   CU(cudaGetLastError());
@@ -689,9 +716,11 @@ int shx_strip_pack_migrants(shx_ctx* c, shx_drop* dev_lo, shx_drop* dev_hi, size
   if (rc) return rc;
   if (!dev_lo || !dev_hi || !n_lo || !n_hi) return fail(SHX_ERR_ARG, "null argument");
   CU(cudaMemsetAsync(c->d_u32 + 2, 0, 2 * sizeof(unsigned), c->stream));
-  strip_pack_migrants_kernel<<<grid_for(c, c->last_n), 256, 0, c->stream>>>(c->d_drops, (unsigned)c->last_n, dev_lo, dev_hi,
-                                                                               (unsigned)cap, c->d_u32 + 2);
-  c->launches++;
+  if (c->last_n) {
+    strip_pack_migrants_kernel<<<grid_for(c, c->last_n), 256, 0, c->stream>>>(c->d_drops, (unsigned)c->last_n, dev_lo, dev_hi,
+                                                                            (unsigned)cap, c->d_u32 + 2);
+    c->launches++;
+  }
   CU(cudaGetLastError());
   unsigned counts[2];
   CU(cudaMemcpyAsync(counts, c->d_u32 + 2, sizeof counts, cudaMemcpyDeviceToHost, c->stream));
@@ -712,5 +741,21 @@ int shx_strip_run_device_drops(shx_ctx* c, const shx_drop* dev_drops, size_t n, 
   if (out) return fetch_stats(c, out);
   return SHX_OK;
 }
+
+#ifdef SHX_PHASE_TIMING
+int shx_debug_set_exp(unsigned flags) {
+  CU(cudaMemcpyToSymbol(g_exp, &flags, sizeof flags));
+  return SHX_OK;
+}
+int shx_debug_phase_timing(unsigned long long* out8, int reset) {
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpyFromSymbol(out8, g_phase_timing, 8 * sizeof(unsigned long long)));
+  if (reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    CU(cudaMemcpyToSymbol(g_phase_timing, z, sizeof z));
+  }
+  return SHX_OK;
+}
+#endif
 
 }  // extern "C"

@@ -14,13 +14,16 @@ namespace shx {
 constexpr int kHeightFracBits = 26;                  // heights are Q5.26 in an int32
 constexpr float kHeightScale = 67108864.0f;          // 2^26
 constexpr float kHeightInv = 1.490116119384765625e-8f;  // 2^-26
-constexpr double kTrackScale = 4294967296.0;         // tracks / sediment ledgers are Q31.32 in an int64
+constexpr float kTrackScale = 1048576.0f;            // 2^20: tracks are Q11.20 in an int32 (|track| < 2048)
+constexpr float kTrackInv = 9.5367431640625e-7f;     // 2^-20
+constexpr float kLedgerScale = 4294967296.0f;        // 2^32: sediment ledgers are Q31.32 in an int64
 
 __device__ __forceinline__ float h_to_float(int32_t v) { return (float)v * kHeightInv; }
 __device__ __forceinline__ int32_t h_quantize(float h) { return __float2int_rn(h * kHeightScale); }
-__device__ __forceinline__ long long t_quantize(float v) { return __double2ll_rn((double)v * kTrackScale); }
-__device__ __forceinline__ long long t_quantize_d(double v) { return __double2ll_rn(v * kTrackScale); }
-__device__ __forceinline__ float t_to_float(long long v) { return (float)((double)v * (1.0 / kTrackScale)); }
+__device__ __forceinline__ int32_t t_quantize(float v) { return __float2int_rn(v * kTrackScale); }
+__device__ __forceinline__ float t_to_float(int32_t v) { return (float)v * kTrackInv; }
+// power-of-two scaling is exact in fp32, so this equals llrint((double)v * 2^32)
+__device__ __forceinline__ long long l_quantize(float v) { return __float2ll_rn(v * kLedgerScale); }
 
 // exp(y) for y in [-17, 0]: k = rint(y*log2e), r = y - k*ln2 (two-piece), degree-6 Taylor, scale by 2^k.
 __device__ __forceinline__ float exp_neg(float y) {

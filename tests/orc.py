@@ -46,7 +46,7 @@ class SeqWorld(C.Structure):
 
 class LsWorld(C.Structure):
     _fields_ = [("p", Params), ("size", C.c_int), ("h", C.POINTER(C.c_int32) * 2), ("field", C.POINTER(C.c_float)),
-                ("track", C.POINTER(C.c_int64)), ("row0", C.c_int), ("row1", C.c_int)]
+                ("track", C.POINTER(C.c_int32)), ("row0", C.c_int), ("row1", C.c_int)]
 
 
 def build_oracle():
@@ -87,7 +87,7 @@ def lib():
         L.orc_ls_make_drops.argtypes = [C.POINTER(LsWorld), C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(Stats)]
         L.orc_ls_run.argtypes = [C.POINTER(LsWorld), C.c_void_p, C.c_size_t, C.POINTER(Stats), C.c_void_p, C.c_int,
                                  C.POINTER(C.c_int)]
-        L.orc_ls_ema.argtypes = [C.POINTER(LsWorld)]
+        L.orc_ls_ema.argtypes = [C.POINTER(LsWorld), C.c_int]
         L.orc_ls_reset_tracks.argtypes = [C.POINTER(LsWorld)]
         L.orc_ls_erode.argtypes = [C.POINTER(LsWorld), C.c_int, C.c_uint64, C.c_uint64, C.POINTER(Stats)]
         L.orc_ls_erode_spawnlist.argtypes = [C.POINTER(LsWorld), C.c_void_p, C.c_size_t, C.POINTER(Stats)]
@@ -231,8 +231,8 @@ class Ls:
         lib().orc_ls_make_drops(self.w, xy.ctypes.data, drops.size, drops.ctypes.data, C.byref(st))
         return drops, st
 
-    def ema(self):
-        lib().orc_ls_ema(self.w)
+    def ema(self, reset=False):
+        return lib().orc_ls_ema(self.w, int(reset))
 
     def reset_tracks(self):
         lib().orc_ls_reset_tracks(self.w)
