@@ -91,9 +91,10 @@ typedef struct {
 } shx_stats;
 
 #define SHX_HEIGHT_FRAC_BITS 26 /* heights: Q5.26 in an int32, |h| < 31 */
-#define SHX_TRACK_FRAC_BITS 20  /* discharge/momentum tracks: Q11.20 in an int32; a call that pushes a
-                                   discharge track past 1024 (about 1024 drop visits of ONE cell) fails
-                                   with SHX_ERR_RANGE instead of wrapping */
+#define SHX_TRACK_FRAC_BITS 18  /* discharge/momentum tracks: Q13.18 in an int32; a call that pushes a
+                                   discharge track past 4096 (about 4096 drop visits of ONE cell; the
+                                   reference's default world peaks near 60) fails with SHX_ERR_RANGE
+                                   instead of wrapping (detection is exact below 16384) */
 #define SHX_LEDGER_FRAC_BITS 32 /* fx_sed_* sums: Q31.32 in an int64 */
 
 enum {
@@ -153,6 +154,14 @@ int shx_download_async(shx_ctx* c, shx_cell* pool, size_t ncells, unsigned field
 int shx_erode(shx_ctx* c, int cycles, uint64_t seed, shx_stats* out /* may be NULL */);
 int shx_erode_async(shx_ctx* c, int cycles, uint64_t seed); /* no host sync; stats via shx_read_stats */
 int shx_read_stats(shx_ctx* c, shx_stats* out);             /* syncs; stats of the last *_async call */
+/* optional per-kernel device timing of shx_erode / shx_erode_async (CUDA events on the context's
+ * stream): sums since the last read, in milliseconds.  shx_timing_read synchronises and resets. */
+typedef struct {
+  double spawn_ms, descend_ms, ema_ms;
+  uint64_t descend_launches; /* timed descend spans (one per erode call) */
+} shx_timing;
+int shx_timing_enable(shx_ctx* c, int on);
+int shx_timing_read(shx_ctx* c, shx_timing* out);
 /* same with explicit spawn points (x,y pairs, world coordinates) -- parity mode */
 int shx_erode_spawnlist(shx_ctx* c, const float* xy, size_t ndrops, shx_stats* out);
 /* one drop, state after every Drop::descend call: 7 floats {age,pos.x,pos.y,speed.x,speed.y,volume,sediment} */
@@ -166,6 +175,9 @@ int shx_run_drops(shx_ctx* c, shx_drop* drops /* host, in/out */, size_t n, shx_
 
 /* sparse push of Plant::root stamps (vegetation.h:87-118): rootdensity[x,y] += delta */
 int shx_add_rootdensity(shx_ctx* c, const int* xy, const float* delta, size_t n);
+/* same, absolute values (rootdensity[x,y] = value); cells must be distinct.  This is what the host adaptor
+ * uses after the unchanged Vegetation::grow() has edited the host pool. */
+int shx_set_rootdensity(shx_ctx* c, const int* xy, const float* value, size_t n);
 
 /* device-side seeded synthetic terrain (value-noise fBm normalised to [0,1]); other fields zeroed */
 int shx_synth_terrain(shx_ctx* c, uint32_t seed);
@@ -174,7 +186,7 @@ int shx_synth_terrain(shx_ctx* c, uint32_t seed);
  * with the lock-step oracle).  Either pointer may be NULL.
  *   hq2:   2 int32 per cell, the two Q5.26 height planes interleaved
  *   rec32: 32 bytes per cell {f32 discharge, momentumx, momentumy, rootdensity,
- *                             i32 Q11.20 discharge_track, momentumx_track, momentumy_track, pad} */
+ *                             i32 Q13.18 discharge_track, momentumx_track, momentumy_track, pad} */
 int shx_download_raw(shx_ctx* c, int32_t* hq2, void* rec32);
 int shx_stored_rows(const shx_ctx* c, int* xlo, int* nrows);
 
@@ -192,6 +204,12 @@ int shx_strip_set_halo(shx_ctx* c, const int32_t* dev_lo, const int32_t* dev_hi)
 int shx_strip_pack_migrants(shx_ctx* c, shx_drop* dev_lo, shx_drop* dev_hi, size_t cap, int* n_lo, int* n_hi);
 /* continue drops received from neighbours (device buffer) until they finish or leave again */
 int shx_strip_run_device_drops(shx_ctx* c, const shx_drop* dev_drops, size_t n, shx_stats* out);
+/* one strip's share of World::erode split around the exchange rounds:
+ *   begin = reset tracks + spawn this strip's nodes + march them (world.h:56-76), no EMA
+ *   end   = EMA of the owned rows (world.h:81-86)
+ * stats accumulate from begin to end (shx_read_stats after end). */
+int shx_strip_erode_begin(shx_ctx* c, int cycles, uint64_t seed);
+int shx_strip_erode_end(shx_ctx* c);
 
 #ifdef __cplusplus
 }

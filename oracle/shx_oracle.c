@@ -15,9 +15,9 @@
 
 /* sediment ledger: Q31.32 (power-of-two scaling is exact in fp32) */
 static int64_t tq(float v) { return (int64_t)llrintf(v * 4294967296.0f); }
-/* track accumulators: Q11.20 in an int32 */
-#define TRACK_SCALE 1048576.0f
-#define TRACK_INV 9.5367431640625e-7f
+/* track accumulators: Q13.18 in an int32 */
+#define TRACK_SCALE 262144.0f
+#define TRACK_INV 3.814697265625e-6f
 static int32_t trq(float v) { return (int32_t)lrintf(v * TRACK_SCALE); }
 static float track_f(int32_t v) { return (float)v * TRACK_INV; }
 static int32_t wrap_add(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
@@ -59,7 +59,7 @@ float orc_erff_libm(float x) { return erff(x); }
  * Coefficients: tools/fit_erf.py (max error 1.47 ulp against the exact erf). */
 static float poly_exp_neg(float y) {
   const float k = rintf(y * 0x1.715476p+0f);
-  float r = y - k * 0x1.62e000p-1f;
+  float r = y - k * 0x1.62e400p-1f;
   r = r - k * 0x1.7f7d1cp-20f;
   float p = 0x1.6c16c2p-10f;
   p = p * r + 0x1.111112p-7f;
@@ -649,7 +649,7 @@ void orc_ls_reset_tracks(orc_ls_world* w) { /* world.h:56-61 */
   memset(w->track, 0, sizeof(orc_track) * (size_t)w->size * w->size);
 }
 
-/* world.h:81-86; returns 1 if a discharge accumulator left the Q11.20 range (the product then
+/* world.h:81-86; returns 1 if a discharge accumulator left the Q13.18 range (the product then
  * reports SHX_ERR_RANGE).  reset != 0 also zeroes the tracks (world.h:56-61 of the next call). */
 int orc_ls_ema(orc_ls_world* w, int reset) {
   int overflow = 0;

@@ -79,7 +79,7 @@ typedef struct {
 } orc_stats;
 
 #define ORC_HEIGHT_FRAC_BITS 26
-#define ORC_TRACK_FRAC_BITS 20
+#define ORC_TRACK_FRAC_BITS 18
 #define ORC_LEDGER_FRAC_BITS 32
 
 void orc_default_params(orc_params* p, int mapsize);
@@ -120,7 +120,7 @@ typedef struct {
   int size;         /* cells per side = mapsize*tilesize */
   int32_t* h[2];    /* height planes, Q5.26, index x*size+y; equal outside a batch */
   float* field;     /* 4 floats per cell: discharge, momentumx, momentumy, rootdensity */
-  orc_track* track; /* Q11.20 accumulators */
+  orc_track* track; /* Q13.18 accumulators */
   int row0, row1;   /* rows [row0,row1) are owned (strip); 0,size for the whole map */
 } orc_ls_world;
 

@@ -26,7 +26,7 @@ MODE_BATCHED, MODE_SEQUENTIAL = 0, 1
 F_HEIGHT, F_DISCHARGE, F_MOMENTUM, F_TRACKS, F_ROOTDENSITY, F_ALL = 1, 2, 4, 8, 16, 31
 DROP_ALIVE, DROP_CASCADE, DROP_DONE_AGE, DROP_DONE_VOL, DROP_DONE_OOB = 1, 2, 4, 8, 16
 DROP_REJECTED, DROP_DONE_NULL, DROP_MIGRATE_LO, DROP_MIGRATE_HI = 32, 64, 128, 256
-HEIGHT_FRAC_BITS, TRACK_FRAC_BITS, LEDGER_FRAC_BITS = 26, 20, 32
+HEIGHT_FRAC_BITS, TRACK_FRAC_BITS, LEDGER_FRAC_BITS = 26, 18, 32
 
 
 class ShxError(RuntimeError):
@@ -57,6 +57,11 @@ class Stats(C.Structure):
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class Timing(C.Structure):
+    _fields_ = [("spawn_ms", C.c_double), ("descend_ms", C.c_double), ("ema_ms", C.c_double),
+                ("descend_launches", C.c_uint64)]
 
 
 _lib = None
@@ -92,6 +97,8 @@ def lib():
     L.shx_erode.argtypes = [vp, C.c_int, u64, C.POINTER(Stats)]
     L.shx_erode_async.argtypes = [vp, C.c_int, u64]
     L.shx_read_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.shx_timing_enable.argtypes = [vp, C.c_int]
+    L.shx_timing_read.argtypes = [vp, C.POINTER(Timing)]
     L.shx_erode_spawnlist.argtypes = [vp, vp, sz, C.POINTER(Stats)]
     L.shx_trace_drop.argtypes = [vp, C.c_float, C.c_float, vp, C.c_int, C.POINTER(C.c_int)]
     L.shx_reset_tracks.argtypes = [vp]
@@ -99,6 +106,7 @@ def lib():
     L.shx_spawn.argtypes = [vp, C.c_int, u64, u64, vp, C.POINTER(sz)]
     L.shx_run_drops.argtypes = [vp, vp, sz, C.POINTER(Stats)]
     L.shx_add_rootdensity.argtypes = [vp, vp, vp, sz]
+    L.shx_set_rootdensity.argtypes = [vp, vp, vp, sz]
     L.shx_synth_terrain.argtypes = [vp, C.c_uint32]
     L.shx_download_raw.argtypes = [vp, vp, vp]
     L.shx_stored_rows.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -108,6 +116,8 @@ def lib():
     L.shx_strip_set_halo.argtypes = [vp, vp, vp]
     L.shx_strip_pack_migrants.argtypes = [vp, vp, vp, sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.shx_strip_run_device_drops.argtypes = [vp, vp, sz, C.POINTER(Stats)]
+    L.shx_strip_erode_begin.argtypes = [vp, C.c_int, u64]
+    L.shx_strip_erode_end.argtypes = [vp]
     _lib = L
     return L
 
@@ -203,6 +213,13 @@ class World:
         track = np.ascontiguousarray(rec[..., 4:])
         return np.ascontiguousarray(hq[..., 0]), np.ascontiguousarray(hq[..., 1]), field, track
 
+    def download_height_q(self):
+        """the interleaved Q5.26 height planes only: int32 array [rows, size, 2]"""
+        _, nrows = self.stored_rows()
+        hq = np.zeros((nrows, self.size, 2), np.int32)
+        self._check(self.L.shx_download_raw(self._h, hq.ctypes.data, None))
+        return hq
+
     def synth_terrain(self, seed):
         self._check(self.L.shx_synth_terrain(self._h, seed))
 
@@ -219,6 +236,14 @@ class World:
         st = Stats()
         self._check(self.L.shx_read_stats(self._h, C.byref(st)))
         return st
+
+    def timing_enable(self, on=True):
+        self._check(self.L.shx_timing_enable(self._h, int(on)))
+
+    def timing_read(self):
+        t = Timing()
+        self._check(self.L.shx_timing_read(self._h, C.byref(t)))
+        return t
 
     def erode_spawnlist(self, xy):
         xy = np.ascontiguousarray(xy, np.float32)
@@ -256,6 +281,11 @@ class World:
         delta = np.ascontiguousarray(delta, np.float32)
         self._check(self.L.shx_add_rootdensity(self._h, xy.ctypes.data, delta.ctypes.data, delta.size))
 
+    def set_rootdensity(self, xy, value):
+        xy = np.ascontiguousarray(xy, np.int32)
+        value = np.ascontiguousarray(value, np.float32)
+        self._check(self.L.shx_set_rootdensity(self._h, xy.ctypes.data, value.ctypes.data, value.size))
+
     # -- strip exchange (device pointers as ints)
     def strip_pack_halo_delta(self, lo, hi):
         self._check(self.L.shx_strip_pack_halo_delta(self._h, lo, hi))
@@ -273,6 +303,12 @@ class World:
         a, b = C.c_int(), C.c_int()
         self._check(self.L.shx_strip_pack_migrants(self._h, lo, hi, cap, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def strip_erode_begin(self, cycles, seed=0):
+        self._check(self.L.shx_strip_erode_begin(self._h, cycles, seed))
+
+    def strip_erode_end(self):
+        self._check(self.L.shx_strip_erode_end(self._h))
 
     def strip_run_device_drops(self, dev_ptr, n, want_stats=True):
         st = Stats()

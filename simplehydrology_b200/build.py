@@ -49,5 +49,24 @@ def build(force=False, verbose=False):
     return LIB
 
 
+HOST_EXAMPLE = os.path.join(HERE, "host", "example_erode")
+
+
+def build_host_example(force=False):
+    """the C++ host adaptor's example driver (plain g++, links libshx.so through the C ABI only)"""
+    src = os.path.join(HERE, "host", "example_erode.cpp")
+    deps = [src, os.path.join(HERE, "host", "shx_world.hpp"), os.path.join(ROOT, "include", "shx.h"), LIB]
+    if not force and os.path.exists(HOST_EXAMPLE) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_EXAMPLE) for d in deps):
+        return HOST_EXAMPLE
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else os.environ.get("CXX", "g++")
+    cmd = [cxx, "-std=c++17", "-O2", "-Wall", src, "-o", HOST_EXAMPLE, "-L" + HERE, "-lshx", "-Wl,-rpath," + HERE]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building the host example")
+    return HOST_EXAMPLE
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_host_example(force="--force" in sys.argv))

@@ -7,8 +7,14 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "shx_kernels.cuh"
+
+struct TimingSpan {
+  int kind;  // 0 spawn, 1 descend, 2 ema
+  cudaEvent_t e0, e1;
+};
 
 using namespace shx;
 
@@ -58,6 +64,9 @@ struct shx_ctx {
   int cap_blocks_big = 0;   // co-resident CTAs of the multi-CTA instantiation at block_big
   int block_big = 256;
   const void* kernel_big = nullptr;
+  bool timing = false;
+  std::vector<TimingSpan> spans;
+  bool strip_open = false;  // between shx_strip_erode_begin and _end
 };
 
 static StepParams step_params(const shx_params& p) {
@@ -388,7 +397,7 @@ static int fetch_stats(shx_ctx* c, shx_stats* out) {
   }
   if (c->h_flags[0]) {
     CU(cudaMemsetAsync(c->d_flags, 0, sizeof(int), c->stream));
-    return fail(SHX_ERR_RANGE, "a discharge track left the Q11.20 range (more than ~1024 drop visits of one cell in one call)");
+    return fail(SHX_ERR_RANGE, "a discharge track left the Q13.18 range (more than ~4096 drop visits of one cell in one call)");
   }
   return SHX_OK;
 }
@@ -510,16 +519,62 @@ static int spawn_device(shx_ctx* c, int cycles, uint64_t seed, uint64_t epoch, s
   return SHX_OK;
 }
 
+// ---- optional per-kernel timing with CUDA events on the context's stream (bench.py's roofline)
+static int span_begin(shx_ctx* c, int kind) {
+  if (!c->timing) return SHX_OK;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  c->spans.push_back({kind, e0, e1});
+  CU(cudaEventRecord(e0, c->stream));
+  return SHX_OK;
+}
+static int span_end(shx_ctx* c) {
+  if (!c->timing) return SHX_OK;
+  CU(cudaEventRecord(c->spans.back().e1, c->stream));
+  return SHX_OK;
+}
+
+int shx_timing_enable(shx_ctx* c, int on) {
+  if (!c) return fail(SHX_ERR_ARG, "null context");
+  c->timing = on != 0;
+  return SHX_OK;
+}
+
+int shx_timing_read(shx_ctx* c, shx_timing* out) {
+  if (!c || !out) return fail(SHX_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->cfg.device));
+  CU(cudaStreamSynchronize(c->stream));
+  memset(out, 0, sizeof(*out));
+  for (auto& s : c->spans) {
+    float ms = 0.0f;
+    CU(cudaEventElapsedTime(&ms, s.e0, s.e1));
+    if (s.kind == 0) out->spawn_ms += ms;
+    else if (s.kind == 1) { out->descend_ms += ms; out->descend_launches++; }
+    else out->ema_ms += ms;
+    cudaEventDestroy(s.e0);
+    cudaEventDestroy(s.e1);
+  }
+  c->spans.clear();
+  return SHX_OK;
+}
+
 int shx_erode_async(shx_ctx* c, int cycles, uint64_t seed) {
   if (!c) return fail(SHX_ERR_ARG, "null context");
   int rc = begin_call(c);
   if (rc) return rc;
   if (!c->tracks_clean && (rc = shx_reset_tracks(c))) return rc;  // world.h:56-61
   size_t n = 0;
+  if ((rc = span_begin(c, 0))) return rc;
   if ((rc = spawn_device(c, cycles, seed, c->epoch, &n))) return rc;  // world.h:64-74
+  if ((rc = span_end(c))) return rc;
   c->epoch++;
+  if ((rc = span_begin(c, 1))) return rc;
   if ((rc = run_device_drops(c, n, false))) return rc;  // world.h:76
-  return ema_launch(c, !c->cfg.keep_tracks);            // world.h:81-86
+  if ((rc = span_end(c))) return rc;
+  if ((rc = span_begin(c, 2))) return rc;
+  if ((rc = ema_launch(c, !c->cfg.keep_tracks))) return rc;  // world.h:81-86
+  return span_end(c);
 }
 
 int shx_read_stats(shx_ctx* c, shx_stats* out) {
@@ -600,7 +655,12 @@ int shx_run_drops(shx_ctx* c, shx_drop* drops, size_t n, shx_stats* out) {
   return fetch_stats(c, out);
 }
 
-int shx_add_rootdensity(shx_ctx* c, const int* xy, const float* delta, size_t n) {
+static int push_rootdensity(shx_ctx* c, const int* xy, const float* delta, size_t n, bool absolute);
+
+int shx_add_rootdensity(shx_ctx* c, const int* xy, const float* delta, size_t n) { return push_rootdensity(c, xy, delta, n, false); }
+int shx_set_rootdensity(shx_ctx* c, const int* xy, const float* value, size_t n) { return push_rootdensity(c, xy, value, n, true); }
+
+static int push_rootdensity(shx_ctx* c, const int* xy, const float* delta, size_t n, bool absolute) {
   if (!c || ((!xy || !delta) && n)) return fail(SHX_ERR_ARG, "null argument");
   if (!n) return SHX_OK;
   CU(cudaSetDevice(c->cfg.device));
@@ -610,7 +670,8 @@ int shx_add_rootdensity(shx_ctx* c, const int* xy, const float* delta, size_t n)
   CU(cudaMallocAsync((void**)&d_delta, n * sizeof(float), c->stream));
   CU(cudaMemcpyAsync(d_xy, xy, n * 2 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(d_delta, delta, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  add_rootdensity_kernel<<<1, 1, 0, c->stream>>>(c->m, d_xy, d_delta, n);
+  if (absolute) set_rootdensity_kernel<<<grid_for(c, n), 256, 0, c->stream>>>(c->m, d_xy, d_delta, n);
+  else add_rootdensity_kernel<<<1, 1, 0, c->stream>>>(c->m, d_xy, d_delta, n);
   c->launches++;
   CU(cudaGetLastError());
   CU(cudaFreeAsync(d_xy, c->stream));
@@ -735,11 +796,39 @@ int shx_strip_run_device_drops(shx_ctx* c, const shx_drop* dev_drops, size_t n, 
   int rc = strip_check(c);
   if (rc) return rc;
   if (n > c->max_drops) return fail(SHX_ERR_CAPACITY, "more drops than max_drops");
-  if ((rc = begin_call(c))) return rc;
+  if (!c->strip_open && (rc = begin_call(c))) return rc;  // inside begin..end the counters keep accumulating
   if (n) CU(cudaMemcpyAsync(c->d_drops, dev_drops, n * sizeof(shx_drop), cudaMemcpyDeviceToDevice, c->stream));
+  if ((rc = span_begin(c, 1))) return rc;
   if ((rc = run_device_drops(c, n, false))) return rc;
+  if ((rc = span_end(c))) return rc;
   if (out) return fetch_stats(c, out);
   return SHX_OK;
+}
+
+int shx_strip_erode_begin(shx_ctx* c, int cycles, uint64_t seed) {
+  if (!c) return fail(SHX_ERR_ARG, "null context");
+  int rc = begin_call(c);
+  if (rc) return rc;
+  c->strip_open = true;
+  if (!c->tracks_clean && (rc = shx_reset_tracks(c))) return rc;  // world.h:56-61
+  size_t n = 0;
+  if ((rc = span_begin(c, 0))) return rc;
+  if ((rc = spawn_device(c, cycles, seed, c->epoch, &n))) return rc;  // world.h:64-74
+  if ((rc = span_end(c))) return rc;
+  c->epoch++;
+  if ((rc = span_begin(c, 1))) return rc;
+  if ((rc = run_device_drops(c, n, false))) return rc;  // world.h:76
+  return span_end(c);
+}
+
+int shx_strip_erode_end(shx_ctx* c) {
+  if (!c) return fail(SHX_ERR_ARG, "null context");
+  CU(cudaSetDevice(c->cfg.device));
+  c->strip_open = false;
+  int rc = span_begin(c, 2);
+  if (rc) return rc;
+  if ((rc = ema_launch(c, !c->cfg.keep_tracks))) return rc;  // world.h:81-86
+  return span_end(c);
 }
 
 #ifdef SHX_PHASE_TIMING

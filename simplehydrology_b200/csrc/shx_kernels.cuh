@@ -6,7 +6,7 @@
 //        the same 32-byte sector, so the adds hit sectors the phase has just read.
 //   rec  32-byte record per cell = one L2 sector:
 //        {discharge, momentumx, momentumy, rootdensity}  fp32, read-only inside erode
-//        {track_d, track_mx, track_my, pad}              int32 Q11.20 accumulators (RED targets)
+//        {track_d, track_mx, track_my, pad}              int32 Q13.18 accumulators (RED targets)
 // Sequential mode stores fp32 heights in hq[].x and fp32 tracks in the record's second half.
 #pragma once
 #include "shx_step.cuh"
@@ -509,7 +509,7 @@ __global__ void make_drops_kernel(const float* xy, unsigned n, const MapView m, 
 // ---------------------------------------------------------------------------------------------
 // K4 (+K1): EMA of the discharge / momentum maps (world.h:81-86) fused with the track reset
 // (world.h:56-61, hoisted from the start of the next call).  Streams the owned rows: 32 B read and
-// 32 B written per cell.  flags[0] is raised if a discharge accumulator left the Q11.20 range.
+// 32 B written per cell.  flags[0] is raised if a discharge accumulator left the Q13.18 range.
 __global__ void ema_kernel(CellRec* __restrict__ rec, size_t n, float lrate, int sequential, int reset, int* flags) {
   const float keep = 1.0f - lrate;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -519,7 +519,7 @@ __global__ void ema_kernel(CellRec* __restrict__ rec, size_t n, float lrate, int
     if (sequential) {
       td = __int_as_float(t.x); tx = __int_as_float(t.y); ty = __int_as_float(t.z);
     } else {
-      if (t.x < 0 || t.x > (1 << 30)) *flags = 1;  // |momentum| <= sqrt(2)*discharge: checking one is enough
+      if (t.x < 0 || t.x > kTrackLimit) *flags = 1;  // |momentum| <= sqrt(2)*discharge: checking one is enough
       td = t_to_float(t.x); tx = t_to_float(t.y); ty = t_to_float(t.z);
     }
     f.x = keep * f.x + lrate * td;
@@ -560,7 +560,7 @@ __global__ void unpack_tile_kernel(const TileArgs a, const shx_cell* __restrict_
       a.m.hq[i] = make_int2(__float_as_int(lo.x), 0);
       reinterpret_cast<float4*>(a.m.rec + i)[1] = make_float4(hi.x, hi.y, hi.z, 0.0f);
     } else {
-      if (!(fabsf(lo.x) < 31.0f) || !(fabsf(hi.x) < 1024.0f)) *a.error_flag = 1;
+      if (!(fabsf(lo.x) < 31.0f) || !(fabsf(hi.x) < 4096.0f)) *a.error_flag = 1;
       const int32_t q = h_quantize(lo.x);
       a.m.hq[i] = make_int2(q, q);
       reinterpret_cast<int4*>(a.m.rec + i)[1] = make_int4(t_quantize(hi.x), t_quantize(hi.y), t_quantize(hi.z), 0);
@@ -594,6 +594,14 @@ __global__ void pack_tile_kernel(const TileArgs a, shx_cell* __restrict__ aos) {
 // ---------------------------------------------------------------------------------------------
 // Plant::root stamps (vegetation.h:87-118).  Applied by ONE thread in list order so that several
 // stamps on one cell add up in the same fp32 order as the host's sequential `+=`.
+__global__ void set_rootdensity_kernel(const MapView m, const int* xy, const float* value, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = xy[2 * i], y = xy[2 * i + 1];
+    if (x < m.xlo || x >= m.xlo + m.nrows || y < 0 || y >= m.size) continue;
+    m.rec[(size_t)(x - m.xlo) * m.size + y].rootdensity = value[i];
+  }
+}
+
 __global__ void add_rootdensity_kernel(const MapView m, const int* xy, const float* delta, size_t n) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   for (size_t i = 0; i < n; i++) {

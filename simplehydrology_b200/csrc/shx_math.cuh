@@ -14,8 +14,9 @@ namespace shx {
 constexpr int kHeightFracBits = 26;                  // heights are Q5.26 in an int32
 constexpr float kHeightScale = 67108864.0f;          // 2^26
 constexpr float kHeightInv = 1.490116119384765625e-8f;  // 2^-26
-constexpr float kTrackScale = 1048576.0f;            // 2^20: tracks are Q11.20 in an int32 (|track| < 2048)
-constexpr float kTrackInv = 9.5367431640625e-7f;     // 2^-20
+constexpr float kTrackScale = 262144.0f;             // 2^18: tracks are Q13.18 in an int32 (|track| < 8192)
+constexpr float kTrackInv = 3.814697265625e-6f;      // 2^-18
+constexpr int kTrackLimit = 1 << 30;                 // a discharge track beyond 4096 is reported as overflow
 constexpr float kLedgerScale = 4294967296.0f;        // 2^32: sediment ledgers are Q31.32 in an int64
 
 __device__ __forceinline__ float h_to_float(int32_t v) { return (float)v * kHeightInv; }
@@ -28,7 +29,7 @@ __device__ __forceinline__ long long l_quantize(float v) { return __float2ll_rn(
 // exp(y) for y in [-17, 0]: k = rint(y*log2e), r = y - k*ln2 (two-piece), degree-6 Taylor, scale by 2^k.
 __device__ __forceinline__ float exp_neg(float y) {
   const float k = rintf(y * 0x1.715476p+0f);
-  float r = y - k * 0x1.62e000p-1f;
+  float r = y - k * 0x1.62e400p-1f;
   r = r - k * 0x1.7f7d1cp-20f;
   float p = 0x1.6c16c2p-10f;
   p = p * r + 0x1.111112p-7f;

@@ -1,0 +1,177 @@
+"""Row-strip decomposition of one world over the GPUs of a box: one process per GPU, one strip of
+rows (constant x, whole tiles) per rank, neighbour-only exchange through torch.distributed.
+
+Per World::erode call (world.h:54-88) every rank
+  1. resets its tracks, spawns the drops of ITS nodes and marches them in lock step until they
+     finish or leave the strip (shx_strip_erode_begin);
+  2. exchange round, repeated until no drop is in flight anywhere:
+       a. the integer height deltas a strip accumulated in its halo rows (cascade transfers across
+          the strip border) go to the owner, which adds them to its edge rows;
+       b. the owners' fresh edge rows come back and refresh the halos;
+       c. drops that left a strip (28-byte Drop record + status word) go to the neighbour, which
+          marches them on (shx_strip_run_device_drops);
+  3. runs the EMA over its own rows (shx_strip_erode_end).
+Only neighbours talk (send/recv); the single collective is the 1-int "anything still in flight?"
+all-reduce.  Everything exchanged is an integer or a bit-copied record, so a k-strip run is
+deterministic for given k.  It is NOT bit-identical to the 1-GPU run: a drop that crosses a border
+pauses until the round ends, i.e. the lock-step schedule differs near borders.  Parity with the
+single-domain result is statistical (tests/test_gpu_strips.py).
+
+The exchange logic is backend-agnostic: `GpuStrip` drives libshx on a CUDA device; tests drive the
+same StripExchange with a CPU stand-in over gloo (tests/test_strips_gloo.py).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class StripExchange:
+    """the per-call protocol; `backend` provides the strip-local operations on torch tensors"""
+
+    def __init__(self, backend, rank, world):
+        self.b, self.rank, self.world = backend, rank, world
+        self.lo = rank - 1 if rank > 0 else None
+        self.hi = rank + 1 if rank < world - 1 else None
+        self.rounds = 0
+
+    def _swap(self, to_lo, to_hi, like_lo, like_hi):
+        """send to_lo/to_hi to the neighbours, receive same-shaped tensors from them"""
+        from_lo = torch.empty_like(like_lo) if self.lo is not None else None
+        from_hi = torch.empty_like(like_hi) if self.hi is not None else None
+        ops = []
+        if self.lo is not None:
+            ops += [dist.P2POp(dist.isend, to_lo, self.lo), dist.P2POp(dist.irecv, from_lo, self.lo)]
+        if self.hi is not None:
+            ops += [dist.P2POp(dist.isend, to_hi, self.hi), dist.P2POp(dist.irecv, from_hi, self.hi)]
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        return from_lo, from_hi
+
+    def exchange_heights(self):
+        d_lo, d_hi = self.b.pack_halo_delta()
+        f_lo, f_hi = self._swap(d_lo, d_hi, d_lo, d_hi)  # lower neighbour's hi-halo covers my first rows
+        self.b.apply_halo_delta(f_lo, f_hi)
+        b_lo, b_hi = self.b.pack_boundary()
+        f_lo, f_hi = self._swap(b_lo, b_hi, b_lo, b_hi)
+        self.b.set_halo(f_lo, f_hi)
+
+    def exchange_drops(self):
+        """returns the number of drops this rank received"""
+        out_lo, out_hi = self.b.pack_migrants()  # [n, 8] int32 records
+        counts = torch.tensor([out_lo.shape[0], out_hi.shape[0]], dtype=torch.int64, device=out_lo.device)
+        z = torch.zeros(2, dtype=torch.int64, device=out_lo.device)
+        c_lo, c_hi = self._swap(counts[:1], counts[1:], z[:1], z[:1])
+        n_lo = int(c_lo.item()) if c_lo is not None else 0  # what the lower neighbour sends up to me
+        n_hi = int(c_hi.item()) if c_hi is not None else 0
+        in_lo = out_lo.new_empty((n_lo, 8))
+        in_hi = out_lo.new_empty((n_hi, 8))
+        ops = []
+        if self.lo is not None:
+            if out_lo.shape[0]:
+                ops.append(dist.P2POp(dist.isend, out_lo, self.lo))
+            if n_lo:
+                ops.append(dist.P2POp(dist.irecv, in_lo, self.lo))
+        if self.hi is not None:
+            if out_hi.shape[0]:
+                ops.append(dist.P2POp(dist.isend, out_hi, self.hi))
+            if n_hi:
+                ops.append(dist.P2POp(dist.irecv, in_hi, self.hi))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        received = torch.cat([in_lo, in_hi]) if (n_lo + n_hi) else in_lo
+        return received
+
+    def erode(self, cycles, seed=0, max_rounds=64):
+        self.b.begin(cycles, seed)
+        self.rounds = 0
+        while True:
+            self.exchange_heights()
+            received = self.exchange_drops()
+            flag = torch.tensor([received.shape[0]], dtype=torch.int64, device=received.device)
+            if self.world > 1:
+                dist.all_reduce(flag)
+            self.rounds += 1
+            if int(flag.item()) == 0:
+                break
+            if self.rounds >= max_rounds:
+                raise RuntimeError("drops still crossing strip borders after max_rounds exchange rounds")
+            self.b.run_drops(received)
+        self.b.end()
+
+
+class GpuStrip:
+    """backend over libshx: one strip context on one CUDA device, buffers are torch CUDA tensors"""
+
+    def __init__(self, mapsize, rank, world, device, halo=2, params=None, drops_per_node=512):
+        import simplehydrology_b200 as shx
+        self.shx = shx
+        p = params if params is not None else shx.default_params(mapsize)
+        size = p.mapsize * p.tilesize
+        tiles = p.mapsize
+        if tiles % world:
+            raise ValueError("the number of tile rows must be divisible by the number of strips")
+        rows = (tiles // world) * p.tilesize
+        self.row0, self.row1 = rank * rows, (rank + 1) * rows
+        self.size, self.halo = size, halo
+        self.dev = torch.device("cuda", device)
+        whole = world == 1
+        nodes = (tiles // world) * tiles
+        self.cap = max(4096, nodes * drops_per_node)
+        self.W = shx.World(params=p, device=device, row0=0 if whole else self.row0, row1=0 if whole else self.row1, halo=halo,
+                           max_drops=self.cap)
+        self.has_lo, self.has_hi = rank > 0, rank < world - 1
+        n = halo * size
+        mk = lambda: torch.zeros(n, dtype=torch.int32, device=self.dev)
+        self.d_lo, self.d_hi, self.b_lo, self.b_hi = mk(), mk(), mk(), mk()
+        self.out_lo = torch.zeros((self.cap, 8), dtype=torch.int32, device=self.dev)
+        self.out_hi = torch.zeros((self.cap, 8), dtype=torch.int32, device=self.dev)
+        self.W.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    @staticmethod
+    def _p(t):
+        return t.data_ptr() if t is not None else None
+
+    def begin(self, cycles, seed):
+        self.W.strip_erode_begin(cycles, seed)
+
+    def end(self):
+        self.W.strip_erode_end()
+
+    def pack_halo_delta(self):
+        self.W.strip_pack_halo_delta(self._p(self.d_lo) if self.has_lo else None, self._p(self.d_hi) if self.has_hi else None)
+        return self.d_lo, self.d_hi
+
+    def apply_halo_delta(self, from_lo, from_hi):
+        self.W.strip_apply_halo_delta(self._p(from_lo), self._p(from_hi))
+
+    def pack_boundary(self):
+        self.W.strip_pack_boundary(self._p(self.b_lo) if self.has_lo else None, self._p(self.b_hi) if self.has_hi else None)
+        return self.b_lo, self.b_hi
+
+    def set_halo(self, lo, hi):
+        self.W.strip_set_halo(self._p(lo), self._p(hi))
+
+    def pack_migrants(self):
+        n_lo, n_hi = self.W.strip_pack_migrants(self.out_lo.data_ptr(), self.out_hi.data_ptr(), self.cap)
+        return self.out_lo[:n_lo], self.out_hi[:n_hi]
+
+    def run_drops(self, records):
+        records = records.contiguous()
+        self.W.strip_run_device_drops(records.data_ptr(), records.shape[0], want_stats=False)
+
+    def stats(self):
+        return self.W.read_stats()
+
+
+def all_reduce_stats(st, device):
+    """sum the counters of a Stats struct over ranks (phases: max)"""
+    names = [n for n, _ in type(st)._fields_]
+    t = torch.tensor([int(getattr(st, n)) for n in names], dtype=torch.int64, device=device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        phases = t[names.index("phases")].clone()
+        dist.all_reduce(t)
+        dist.all_reduce(phases, op=dist.ReduceOp.MAX)
+        t[names.index("phases")] = phases
+    return dict(zip(names, [int(v) for v in t.tolist()]))

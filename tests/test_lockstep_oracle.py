@@ -1,0 +1,114 @@
+"""Properties of the lock-step (batched, fixed-point) restatement orc_ls_* -- the bit-exact checker
+of the CUDA path.  It applies the same per-step arithmetic as the sequential oracle under the
+batched schedule, so: one drop alone behaves like the reference up to fixed-point rounding, the
+result is independent of drop order, and the integer mass ledger closes exactly."""
+import numpy as np
+
+import orc
+
+H_LSB = 2.0 ** -26
+
+
+def test_single_drop_follows_the_reference_until_rounding_separates_them(init_cells):
+    p = orc.default_params(1)
+    for (x, y) in [(256.0, 256.0), (100.0, 300.0), (37.75, 129.5)]:
+        S = orc.Seq(init_cells.copy(), erf_poly=True)
+        ls = orc.Ls(p)
+        ls.upload(init_cells)
+        a = S.trace_drop(x, y)
+        drops, _ = ls.make_drops(np.array([[x, y]], np.float32))
+        st, b = ls.run_drops(drops, trace_cap=1024)
+        n = 64  # first 64 steps: heights differ by <= a few 2^-26, positions by <= 1e-3 cell
+        assert len(a) >= n and len(b) >= n
+        assert np.abs(a[:n, 1:3] - b[:n, 1:3]).max() < 1e-3
+        assert np.abs(a[:n, 5] - b[:n, 5]).max() == 0.0  # volume: identical arithmetic
+        assert np.abs(a[:n, 6] - b[:n, 6]).max() < 1e-6
+        assert np.array_equal(ls.height_q(0), ls.height_q(1))  # planes agree outside a run
+
+
+def test_height_quantisation_roundtrip():
+    L = orc.lib()
+    for h in [0.0, 1.0, 0.5, 0.1, 0.3333333, -0.25, 30.99]:
+        q = L.orc_ls_quantize_height(h)
+        assert abs(q * H_LSB - np.float32(h)) <= H_LSB / 2 + 1e-12
+
+
+def test_order_independence_and_determinism(init_cells):
+    p = orc.default_params(1)
+    rng = np.random.default_rng(21)
+    xy = rng.integers(0, 512, size=(300, 2)).astype(np.float32)
+    results = []
+    for perm in (np.arange(300), rng.permutation(300), rng.permutation(300)):
+        ls = orc.Ls(p)
+        ls.upload(init_cells)
+        st = ls.erode_spawnlist(xy[perm])
+        results.append((ls.height_q(0).copy(), ls.field().copy(), st.as_dict()))
+    for h, f, st in results[1:]:
+        assert np.array_equal(h, results[0][0])
+        assert np.array_equal(f.view(np.uint32), results[0][1].view(np.uint32))
+        assert st == results[0][2]
+
+
+def test_integer_mass_ledger_closes_exactly(init_cells):
+    p = orc.default_params(1)
+    ls = orc.Ls(p)
+    ls.upload(init_cells)
+    rng = np.random.default_rng(5)
+    for _ in range(3):
+        before = ls.height_q(0).astype(np.int64).sum()
+        st = ls.erode_spawnlist(rng.integers(0, 512, size=(400, 2)).astype(np.float32))
+        after = ls.height_q(0).astype(np.int64).sum()
+        assert after - before == st.fx_deposited - st.fx_eroded
+        assert st.spawned == st.term_age + st.term_vol + st.term_oob
+        # sediment budget of the drops (water.h:131,135,139-142): eroded + inflation = deposited + lost,
+        # up to one rounding (2^-27) per step of the fp32 sediment against its Q5.26 image
+        lhs = st.fx_eroded * H_LSB + st.fx_sed_inflation * 2.0 ** -32
+        rhs = (st.fx_sed_deposited + st.fx_sed_oob_lost) * 2.0 ** -32
+        assert abs(lhs - rhs) <= st.steps * H_LSB
+
+
+def test_spawn_is_per_node_and_in_tile():
+    p = orc.default_params(4)
+    ls = orc.Ls(p)
+    xy = ls.spawn(99, 0, 64)
+    assert xy.shape == (16 * 64, 2)
+    node = np.repeat(np.arange(16), 64)
+    assert np.array_equal((xy[:, 0] // 512).astype(int), node // 4)  # cellpool.h:327-333 node origin
+    assert np.array_equal((xy[:, 1] // 512).astype(int), node % 4)
+    assert np.array_equal(xy, np.floor(xy))
+    again = ls.spawn(99, 0, 64)
+    other = ls.spawn(99, 1, 64)
+    assert np.array_equal(xy, again) and not np.array_equal(xy, other)
+
+
+def test_rejection_and_out_of_map_spawns(init_cells):
+    p = orc.default_params(1)
+    ls = orc.Ls(p)
+    ls.upload(init_cells)
+    h = orc.tiled_to_planar(p, init_cells)
+    low = np.argwhere(h < 0.1)[:5].astype(np.float32)
+    xy = np.concatenate([low, [[-3.0, 10.0], [600.0, 2.0], [255.0, 255.0]]]).astype(np.float32)
+    drops, st = ls.make_drops(xy)
+    assert st.rejected == 7 and st.spawned == 1  # world.h:71-72: height() of a missing cell is 0 < 0.1
+    assert list(drops["flags"][:7]) == [orc.DROP_REJECTED] * 7 and drops["flags"][7] == orc.DROP_ALIVE
+
+
+def test_track_overflow_is_reported():
+    p = orc.default_params(1)
+    ls = orc.Ls(p)
+    cells = np.zeros(512 * 512, orc.CELL_DTYPE)
+    cells["height"] = 0.5
+    cells["discharge_track"][7] = 3000.0
+    ls.upload(cells)
+    assert ls.ema(reset=False) == 0
+    cells["discharge_track"][7] = 5000.0  # beyond 4096: outside the guaranteed Q13.18 range
+    ls.upload(cells)
+    assert ls.ema(reset=False) == 1
+
+
+def test_synth_terrain_is_normalised_and_seeded():
+    a = orc.synth_terrain(256, 1)
+    b = orc.synth_terrain(256, 1)
+    c = orc.synth_terrain(256, 2)
+    assert a.min() == 0.0 and a.max() == 1.0 and np.array_equal(a, b) and not np.array_equal(a, c)
+    assert 0.3 < a.mean() < 0.7
