@@ -13,12 +13,27 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* float -> fixed point, round to nearest even, SATURATING, NaN -> 0: the semantics of the GPU's
+ * cvt.rni.s32.f32 / cvt.rni.s64.f32, so that even a world that has blown up numerically (heights
+ * beyond the Q5.26 range) stays comparable bit for bit.  Sums then wrap (two's complement). */
+static int32_t sat32(float v) {
+  if (v != v) return 0;
+  if (v >= 2147483648.0f) return INT32_MAX;
+  if (v <= -2147483648.0f) return INT32_MIN;
+  return (int32_t)lrintf(v);
+}
+static int64_t sat64(float v) {
+  if (v != v) return 0;
+  if (v >= 9223372036854775808.0f) return INT64_MAX;
+  if (v <= -9223372036854775808.0f) return INT64_MIN;
+  return (int64_t)llrintf(v);
+}
 /* sediment ledger: Q31.32 (power-of-two scaling is exact in fp32) */
-static int64_t tq(float v) { return (int64_t)llrintf(v * 4294967296.0f); }
+static int64_t tq(float v) { return sat64(v * 4294967296.0f); }
 /* track accumulators: Q13.18 in an int32 */
 #define TRACK_SCALE 262144.0f
 #define TRACK_INV 3.814697265625e-6f
-static int32_t trq(float v) { return (int32_t)lrintf(v * TRACK_SCALE); }
+static int32_t trq(float v) { return sat32(v * TRACK_SCALE); }
 static float track_f(int32_t v) { return (float)v * TRACK_INV; }
 static int32_t wrap_add(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
 
@@ -349,7 +364,7 @@ int orc_seq_trace_drop(orc_seq_world* w, float x, float y, float* trace, int max
 #define HSCALE 67108864.0f           /* 2^26 */
 #define HINV 1.490116119384765625e-8f /* 2^-26 */
 
-int32_t orc_ls_quantize_height(float h) { return (int32_t)lrintf(h * HSCALE); }
+int32_t orc_ls_quantize_height(float h) { return sat32(h * HSCALE); }
 static float hf(int32_t v) { return (float)v * HINV; }
 orc_ls_world* orc_ls_create(const orc_params* p) {
   orc_ls_world* w = (orc_ls_world*)calloc(1, sizeof(*w));
@@ -575,9 +590,9 @@ static int ls_step(orc_ls_world* w, const int32_t* R, orc_drop* d, int32_t* D, i
   const float e = effD * cdiff;
   d->sediment += e; /* :131 */
   {
-    const int32_t q = orc_ls_quantize_height(e); /* :132 */
-    D[4] -= q;
-    st->fx_eroded += q;
+    const int32_t q = orc_ls_quantize_height(-e); /* :132: height += -(effD*cdiff), quantised once */
+    D[4] += q;
+    st->fx_eroded -= q;
   }
   const float carried = d->sediment;
   d->sediment = (float)((double)d->sediment / (1.0 - (double)P->evapRate)); /* :135 */

@@ -83,7 +83,7 @@ class StripExchange:
         received = torch.cat([in_lo, in_hi]) if (n_lo + n_hi) else in_lo
         return received
 
-    def erode(self, cycles, seed=0, max_rounds=64):
+    def erode(self, cycles, seed=0, max_rounds=1024):
         self.b.begin(cycles, seed)
         self.rounds = 0
         while True:
@@ -99,6 +99,54 @@ class StripExchange:
                 raise RuntimeError("drops still crossing strip borders after max_rounds exchange rounds")
             self.b.run_drops(received)
         self.b.end()
+
+
+class LocalStripSet:
+    """k strips held by ONE process (e.g. k logical strips on one GPU): the same protocol as
+    StripExchange with the neighbour transport replaced by handing tensors over directly.  Used to
+    validate the strip kernels against the single-domain run without a multi-GPU box."""
+
+    def __init__(self, backends):
+        self.b = list(backends)
+        self.rounds = 0
+
+    def _exchange_heights(self):
+        k = len(self.b)
+        deltas = [b.pack_halo_delta() for b in self.b]
+        deltas = [(lo.clone(), hi.clone()) for lo, hi in deltas]
+        for i, b in enumerate(self.b):
+            b.apply_halo_delta(deltas[i - 1][1] if i > 0 else None, deltas[i + 1][0] if i < k - 1 else None)
+        bnds = [b.pack_boundary() for b in self.b]
+        bnds = [(lo.clone(), hi.clone()) for lo, hi in bnds]
+        for i, b in enumerate(self.b):
+            b.set_halo(bnds[i - 1][1] if i > 0 else None, bnds[i + 1][0] if i < k - 1 else None)
+
+    def erode(self, cycles, seed=0, max_rounds=1024):
+        k = len(self.b)
+        for b in self.b:
+            b.begin(cycles, seed)
+        self.rounds = 0
+        while True:
+            self._exchange_heights()
+            outs = [b.pack_migrants() for b in self.b]
+            outs = [(lo.clone(), hi.clone()) for lo, hi in outs]
+            inbox = []
+            for i in range(k):
+                parts = []
+                if i > 0 and outs[i - 1][1].shape[0]:
+                    parts.append(outs[i - 1][1])
+                if i < k - 1 and outs[i + 1][0].shape[0]:
+                    parts.append(outs[i + 1][0])
+                inbox.append(torch.cat(parts) if parts else outs[i][0][:0])
+            self.rounds += 1
+            if sum(x.shape[0] for x in inbox) == 0:
+                break
+            if self.rounds >= max_rounds:
+                raise RuntimeError("drops still crossing strip borders after max_rounds exchange rounds")
+            for b, rec in zip(self.b, inbox):
+                b.run_drops(rec)
+        for b in self.b:
+            b.end()
 
 
 class GpuStrip:
