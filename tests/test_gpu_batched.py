@@ -27,6 +27,7 @@ def assert_stats_equal(st, so):
 
 
 def make_world(cells, params, **kw):
+    kw.setdefault("max_drops", 4096)
     W = shx.World(params=shx.Params.from_buffer_copy(bytes(params)), **kw)
     W.upload(cells)
     ls = orc.Ls(params)
@@ -174,7 +175,7 @@ def test_run_to_run_determinism(init_cells):
     xys = [rng.integers(0, 512, size=(2048, 2)).astype(np.float32) for _ in range(3)]
     out = []
     for rep in range(2):
-        with shx.World(mapsize=1) as W:
+        with shx.World(mapsize=1, max_drops=4096) as W:
             W.upload(init_cells)
             for xy in xys:
                 W.erode_spawnlist(xy)
@@ -188,7 +189,7 @@ def test_drop_order_does_not_matter(init_cells):
     xy = rng.integers(0, 512, size=(3000, 2)).astype(np.float32)
     out = []
     for perm in (np.arange(3000), rng.permutation(3000)):
-        with shx.World(mapsize=1) as W:
+        with shx.World(mapsize=1, max_drops=4096) as W:
             W.upload(init_cells)
             W.erode_spawnlist(xy[perm])
             out.append(W.download_raw())

@@ -60,7 +60,7 @@ def test_check1_single_drop_matches_reference(golden, init_cells):
 
 
 def test_check2_mass_ledger(init_cells):
-    with shx.World(mapsize=1) as W:
+    with shx.World(mapsize=1, max_drops=4096) as W:
         W.upload(init_cells)
         rng = np.random.default_rng(4)
         for _ in range(3):
