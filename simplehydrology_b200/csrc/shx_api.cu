@@ -90,13 +90,17 @@ static int grid_for(const shx_ctx* c, size_t n, int block = 256) {
   return (int)std::max<size_t>(1, std::min(want, cap));
 }
 
-static size_t descend_smem(int block) { return (size_t)(9 + 16) * sizeof(int32_t) * block; }
+// s_B[9] + s_D[2][8] + s_S[8] x 2 words, per thread
+static size_t descend_smem(int block) { return (size_t)(9 + 16 + 16) * sizeof(int32_t) * block; }
 
 // Instantiations {max CTA threads, min CTAs/SM}.  KERNEL_SMALL: one CTA of up to 1024 threads for
 // small batches (the barrier is a plain __syncthreads).  Multi-CTA: the first four cap registers at
-// 64 (1024 threads per SM); variant 1 allows 128 registers (512 threads per SM).
+// 64 (1024 threads per SM); variant 1 allows 128 registers (512 threads per SM); variant 2 is
+// 7 CTAs of 128 threads per SM = 896 threads at 72 registers, just enough for the 886 drops per SM
+// of an 8192^2 cycle.
 #define KERNEL_SMALL descend_lockstep_kernel<1024, 1>
 static const void* big_kernel(int block, int variant) {
+  if (variant == 2) return (const void*)descend_lockstep_kernel<128, 7>;
   if (variant == 1) return block <= 256 ? (const void*)descend_lockstep_kernel<256, 2> : (const void*)descend_lockstep_kernel<512, 1>;
   if (block <= 128) return (const void*)descend_lockstep_kernel<128, 8>;
   if (block <= 256) return (const void*)descend_lockstep_kernel<256, 4>;
@@ -222,6 +226,7 @@ int shx_create(shx_ctx** out, const shx_params* p, const shx_config* cfg_in) {
 
   c->block_big = cfg.block_threads > 0 ? std::min(1024, (cfg.block_threads + 31) / 32 * 32) : 256;
   if (cfg.variant == 1) c->block_big = std::min(c->block_big, 512);
+  if (cfg.variant == 2) c->block_big = std::min(c->block_big, 128);
   c->kernel_big = big_kernel(c->block_big, cfg.variant);
   int nb = 0;
   if (cudaFuncSetAttribute(KERNEL_SMALL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)descend_smem(1024)) != cudaSuccess ||

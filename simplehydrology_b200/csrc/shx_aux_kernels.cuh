@@ -1,0 +1,284 @@
+// shx CUDA kernels, part 2 (included by shx_kernels.cuh): spawn, EMA/reset, boundary conversion of the
+// tiled AoS pool, rootdensity pushes, synthetic terrain, row-strip exchange helpers.
+#pragma once
+
+namespace shx {
+
+// ---------------------------------------------------------------------------------------------
+// K2: spawn.  world.h:64-74 with rand() replaced by a counter-based hash keyed
+// (seed, epoch, node, i): node-major, `cycles` drops per node, reject where height < 0.1.
+// node0/nnodes select the nodes of this strip (all of them for a whole map).
+struct SpawnArgs {
+  MapView m;
+  int sequential;
+  int tilesize, mapsize;
+  unsigned node0, nnodes;
+  int cycles;
+  uint64_t key;
+  shx_drop* drops;
+  float* xy;  // optional copy of the positions
+  unsigned long long* stats;
+};
+
+__device__ __forceinline__ shx_drop make_drop(float x, float y, const MapView& m, int sequential, unsigned long long* stats) {
+  shx_drop d = {x, y, 0.0f, 0.0f, 1.0f, 0.0f, 0, SHX_DROP_ALIVE};  // water.h:14-23
+  const int ix = (int)x, iy = (int)y;
+  const bool oob = !(x > -1.0f) || !(y > -1.0f) || ix >= m.size || iy >= m.size;
+  if (!oob && (ix < m.row0 || ix >= m.row1)) {  // not this strip's drop
+    d.flags = 0;
+    return d;
+  }
+  float h = 0.0f;  // map.height() of a missing cell (cellpool.h:433-437)
+  if (!oob) {
+    const int2 hv = m.hq[(ix - m.xlo) * m.size + iy];
+    h = sequential ? __int_as_float(hv.x) : h_to_float(hv.x);
+  }
+  if (!above_tenth(h)) {  // world.h:71-72  (double)h < 0.1
+    d.flags = SHX_DROP_REJECTED;
+    atomicAdd(stats + ST_REJECTED, 1ull);
+  } else {
+    atomicAdd(stats + ST_SPAWNED, 1ull);
+  }
+  return d;
+}
+
+__global__ void spawn_kernel(const SpawnArgs a) {
+  const unsigned n = a.nnodes * (unsigned)a.cycles;
+  for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const unsigned node = a.node0 + k / (unsigned)a.cycles, i = k % (unsigned)a.cycles;
+    const uint64_t r = mix64(a.key + (((uint64_t)node << 32) | (uint64_t)i));
+    const int nx = (int)(node / (unsigned)a.mapsize) * a.tilesize, ny = (int)(node % (unsigned)a.mapsize) * a.tilesize;
+    const float x = (float)(nx + (int)((uint32_t)r % (uint32_t)a.tilesize));
+    const float y = (float)(ny + (int)((uint32_t)(r >> 32) % (uint32_t)a.tilesize));
+    if (a.xy) { a.xy[2 * k] = x; a.xy[2 * k + 1] = y; }
+    a.drops[k] = make_drop(x, y, a.m, a.sequential, a.stats);
+  }
+}
+
+__global__ void make_drops_kernel(const float* xy, unsigned n, const MapView m, int sequential, shx_drop* drops,
+                                  unsigned long long* stats) {
+  for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+    drops[k] = make_drop(xy[2 * k], xy[2 * k + 1], m, sequential, stats);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4 (+K1): EMA of the discharge / momentum maps (world.h:81-86) fused with the track reset
+// (world.h:56-61, hoisted from the start of the next call).  Streams the owned rows: 32 B read and
+// 32 B written per cell.  flags[0] is raised if a discharge accumulator left the Q13.18 range.
+__global__ void ema_kernel(CellRec* __restrict__ rec, size_t n, float lrate, int sequential, int reset, int* flags) {
+  const float keep = 1.0f - lrate;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float4 f = reinterpret_cast<const float4*>(rec + i)[0];
+    int4 t = reinterpret_cast<const int4*>(rec + i)[1];
+    float td, tx, ty;
+    if (sequential) {
+      td = __int_as_float(t.x); tx = __int_as_float(t.y); ty = __int_as_float(t.z);
+    } else {
+      if (t.x < 0 || t.x > kTrackLimit) *flags = 1;  // |momentum| <= sqrt(2)*discharge: checking one is enough
+      td = t_to_float(t.x); tx = t_to_float(t.y); ty = t_to_float(t.z);
+    }
+    f.x = keep * f.x + lrate * td;
+    f.y = keep * f.y + lrate * tx;
+    f.z = keep * f.z + lrate * ty;
+    reinterpret_cast<float4*>(rec + i)[0] = f;
+    if (reset) reinterpret_cast<int4*>(rec + i)[1] = make_int4(0, 0, 0, 0);
+  }
+}
+
+__global__ void reset_tracks_kernel(CellRec* __restrict__ rec, size_t n) {  // world.h:56-61
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    reinterpret_cast<int4*>(rec + i)[1] = make_int4(0, 0, 0, 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Boundary conversion: one 512^2 tile of the host's tiled AoS pool (32 B quad::cell records,
+// x-major inside the tile) <-> the device layout.  Thread per cell; both sides coalesced
+// (consecutive threads = consecutive y).
+struct TileArgs {
+  MapView m;
+  int sequential;
+  int tilesize, tx0, ty0;  // tile origin in world cells
+  int* error_flag;
+};
+
+__global__ void unpack_tile_kernel(const TileArgs a, const shx_cell* __restrict__ aos) {
+  const int ts = a.tilesize;
+  const int n = ts * ts;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+    const int x = a.tx0 + c / ts, y = a.ty0 + c % ts;
+    if (x < a.m.xlo || x >= a.m.xlo + a.m.nrows) continue;
+    const float4 lo = reinterpret_cast<const float4*>(aos + c)[0];  // height discharge momentumx momentumy
+    const float4 hi = reinterpret_cast<const float4*>(aos + c)[1];  // tracks x3, rootdensity
+    const size_t i = (size_t)(x - a.m.xlo) * a.m.size + y;
+    reinterpret_cast<float4*>(a.m.rec + i)[0] = make_float4(lo.y, lo.z, lo.w, hi.w);
+    if (a.sequential) {
+      a.m.hq[i] = make_int2(__float_as_int(lo.x), 0);
+      reinterpret_cast<float4*>(a.m.rec + i)[1] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+    } else {
+      if (!(fabsf(lo.x) < 31.0f) || !(fabsf(hi.x) < 4096.0f)) *a.error_flag = 1;
+      const int32_t q = h_quantize(lo.x);
+      a.m.hq[i] = make_int2(q, q);
+      reinterpret_cast<int4*>(a.m.rec + i)[1] = make_int4(t_quantize(hi.x), t_quantize(hi.y), t_quantize(hi.z), 0);
+    }
+  }
+}
+
+__global__ void pack_tile_kernel(const TileArgs a, shx_cell* __restrict__ aos) {
+  const int ts = a.tilesize;
+  const int n = ts * ts;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+    const int x = a.tx0 + c / ts, y = a.ty0 + c % ts;
+    if (x < a.m.row0 || x >= a.m.row1) continue;
+    const size_t i = (size_t)(x - a.m.xlo) * a.m.size + y;
+    const float4 f = reinterpret_cast<const float4*>(a.m.rec + i)[0];
+    const int4 t = reinterpret_cast<const int4*>(a.m.rec + i)[1];
+    const int2 hv = a.m.hq[i];
+    float4 lo, hi;
+    if (a.sequential) {
+      lo = make_float4(__int_as_float(hv.x), f.x, f.y, f.z);
+      hi = make_float4(__int_as_float(t.x), __int_as_float(t.y), __int_as_float(t.z), f.w);
+    } else {
+      lo = make_float4(h_to_float(hv.x), f.x, f.y, f.z);
+      hi = make_float4(t_to_float(t.x), t_to_float(t.y), t_to_float(t.z), f.w);
+    }
+    reinterpret_cast<float4*>(aos + c)[0] = lo;
+    reinterpret_cast<float4*>(aos + c)[1] = hi;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Plant::root stamps (vegetation.h:87-118).  Applied by ONE thread in list order so that several
+// stamps on one cell add up in the same fp32 order as the host's sequential `+=`.
+__global__ void set_rootdensity_kernel(const MapView m, const int* xy, const float* value, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = xy[2 * i], y = xy[2 * i + 1];
+    if (x < m.xlo || x >= m.xlo + m.nrows || y < 0 || y >= m.size) continue;
+    m.rec[(size_t)(x - m.xlo) * m.size + y].rootdensity = value[i];
+  }
+}
+
+__global__ void add_rootdensity_kernel(const MapView m, const int* xy, const float* delta, size_t n) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  for (size_t i = 0; i < n; i++) {
+    const int x = xy[2 * i], y = xy[2 * i + 1];
+    if (x < m.xlo || x >= m.xlo + m.nrows || y < 0 || y >= m.size) continue;  // getCell() == NULL -> skipped
+    float* w = &m.rec[(size_t)(x - m.xlo) * m.size + y].rootdensity;
+    *w = *w + delta[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Synthetic seeded terrain: hash-lattice value noise, 8 octaves (wavelength 256..2 cells,
+// amplitude 0.6^o -- the reference's layer weights, cellpool.h:361-376), then the reference's
+// min/max normalisation (cellpool.h:382-408).  Same arithmetic as oracle orc_synth_terrain.
+__device__ __forceinline__ uint32_t hash2(uint32_t x, uint32_t y, uint32_t s) {
+  uint32_t h = x * 0x9E3779B1u ^ y * 0x85EBCA77u ^ s * 0xC2B2AE3Du;
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+  return h;
+}
+__device__ __forceinline__ float lattice(uint32_t x, uint32_t y, uint32_t s) {
+  return (float)(hash2(x, y, s) >> 8) * (1.0f / 8388608.0f) - 1.0f;
+}
+__device__ __forceinline__ float synth_raw(int x, int y, uint32_t seed) {
+  float sum = 0.0f, amp = 0.6f;
+  int cell = 256;
+#pragma unroll 1
+  for (int o = 0; o < 8; o++) {
+    const int gx = x / cell, gy = y / cell;
+    const float fx = (float)(x % cell) / (float)cell, fy = (float)(y % cell) / (float)cell;
+    const float ux = fx * fx * (3.0f - 2.0f * fx), uy = fy * fy * (3.0f - 2.0f * fy);
+    const uint32_t s = seed * 8u + (uint32_t)o;
+    const float v00 = lattice((uint32_t)gx, (uint32_t)gy, s), v01 = lattice((uint32_t)gx, (uint32_t)gy + 1u, s);
+    const float v10 = lattice((uint32_t)gx + 1u, (uint32_t)gy, s), v11 = lattice((uint32_t)gx + 1u, (uint32_t)gy + 1u, s);
+    const float p = v00 + (v01 - v00) * uy, q = v10 + (v11 - v10) * uy;
+    sum = sum + amp * (p + (q - p) * ux);
+    amp = amp * 0.6f;
+    cell >>= 1;
+  }
+  return sum;
+}
+
+// pass 1: global min/max over the WHOLE map (every strip computes the same pair)
+__global__ void synth_minmax_kernel(int size, uint32_t seed, unsigned* mnmx) {
+  unsigned mn = 0xffffffffu, mx = 0u;
+  const size_t n = (size_t)size * size;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const unsigned o = f2ord(synth_raw((int)(i / size), (int)(i % size), seed) + 0.0f);
+    mn = min(mn, o);
+    mx = max(mx, o);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(mnmx, mn);
+    atomicMax(mnmx + 1, mx);
+  }
+}
+
+// pass 2: normalise and store (heights both planes; all other fields zero)
+__global__ void synth_fill_kernel(const MapView m, int sequential, uint32_t seed, const unsigned* mnmx) {
+  const float mn = ord2f(mnmx[0]), mx = ord2f(mnmx[1]);
+  const float range = mx - mn;
+  const size_t n = (size_t)m.nrows * m.size;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = m.xlo + (int)(i / m.size), y = (int)(i % m.size);
+    const float h = (synth_raw(x, y, seed) - mn) / range;
+    reinterpret_cast<int4*>(m.rec + i)[0] = make_int4(0, 0, 0, 0);
+    reinterpret_cast<int4*>(m.rec + i)[1] = make_int4(0, 0, 0, 0);
+    if (sequential) {
+      m.hq[i] = make_int2(__float_as_int(h), 0);
+    } else {
+      const int32_t q = h_quantize(h);
+      m.hq[i] = make_int2(q, q);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row-strip exchange helpers (multi-GPU).  A strip keeps `halo` rows of its neighbours' heights on
+// each side.  Cascade transfers of drops on the strip's boundary rows land in those halo rows;
+// `halo_ref` remembers what the halo held at the last refresh, so (current - ref) is exactly the
+// integer amount this strip owes the owner.  Outside a run both planes are equal: plane 0 is used.
+__global__ void strip_halo_delta_kernel(const int2* cur, const int32_t* ref, int32_t* out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = cur[i].x - ref[i];
+}
+__global__ void strip_add_rows_kernel(int2* h, const int32_t* delta, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int32_t v = delta[i];
+    if (v) {
+      int2 c = h[i];
+      c.x += v; c.y += v;
+      h[i] = c;
+    }
+  }
+}
+__global__ void strip_get_rows_kernel(const int2* h, int32_t* out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = h[i].x;
+}
+__global__ void strip_set_rows_kernel(int2* h, int32_t* ref, const int32_t* src, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int32_t v = src[i];
+    h[i] = make_int2(v, v);
+    ref[i] = v;
+  }
+}
+// compact the drops that left the strip into two outboxes (order is irrelevant to the result:
+// every scatter downstream is an integer add)
+__global__ void strip_pack_migrants_kernel(const shx_drop* drops, unsigned n, shx_drop* lo, shx_drop* hi, unsigned cap,
+                                           unsigned* counts) {
+  for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    shx_drop d = drops[k];
+    if (d.flags & (SHX_DROP_MIGRATE_LO | SHX_DROP_MIGRATE_HI)) {
+      const bool tolo = (d.flags & SHX_DROP_MIGRATE_LO) != 0;
+      const unsigned slot = atomicAdd(counts + (tolo ? 0 : 1), 1u);
+      d.flags = (d.flags & ~(SHX_DROP_MIGRATE_LO | SHX_DROP_MIGRATE_HI)) | SHX_DROP_ALIVE;
+      if (slot < cap) (tolo ? lo : hi)[slot] = d;
+    }
+  }
+}
+
+}  // namespace shx

@@ -6,11 +6,16 @@
 //   quad::_normal    source/cellpool.h:181-204
 //   map::height/oob  source/cellpool.h:413-437, node::discharge :242-244
 //
-// Phase = "the World::cascade owed by the previous descend call, then one descend call".  In the
-// reference, descend ends with cascade(pos) at the NEW position and the next descend starts by
-// reading the normal at that same position with nothing in between, so fusing them reads one
-// 3x3 block of heights per step instead of two, and every height change of a phase (cascade
-// transfers, erosion/deposition at the centre, the final sediment drop) lands inside that block.
+// One Drop::descend call is split where it touches memory:
+//   move_math      water.h:70-117   normal -> termination checks -> forces -> fixed-length move -> track amounts
+//   exchange_math  water.h:120-136  sediment exchange with the OLD cell against the NEW cell's height, evaporation
+// followed by water.h:139-154 (out-of-bounds stop, cascade at the new cell, age++).
+//
+// Sequential mode runs them back to back like the reference.  The batched mode defers exchange_math
+// of step k to the start of phase k+1: the new cell's height it needs (water.h:124) is then the
+// centre of the block that phase loads anyway, which removes the only dependent second gather of a
+// step.  For one drop the order of effects is unchanged: exchange(k) -> cascade at the new cell ->
+// move(k+1), exactly water.h:127-154 followed by the next call.
 #pragma once
 #include "../../include/shx.h"
 #include "shx_math.cuh"
@@ -33,23 +38,27 @@ struct DropRegs {
 // (world.h:71,144 compare a float height against a double literal)
 __device__ __forceinline__ bool above_tenth(float h) { return h >= 0.1f; }
 
-struct StepResult {
-  float dheight;        // fp32 amount to ADD to the centre cell's height (water.h:75,80,132)
-  float t_d, t_mx, t_my;  // track deposits at the old cell (water.h:115-117), valid if `moved`
-  bool moved;           // false for the terminating call of an aged-out drop
+struct MoveResult {
+  bool moved;             // false: the call terminated by age / volume (water.h:74-82), dheight = +sediment
+  bool oob;               // new position outside the map (water.h:121,139)
+  float dheight;          // termination only: fp32 amount to ADD to the centre cell
+  float t_d, t_mx, t_my;  // track deposits at the old cell (water.h:115-117)
+  float cap;              // 1 + entrainment*erf(0.4*discharge) of the old cell (water.h:127)
+  float effD;             // depositionRate*(1-rootdensity), clamped (water.h:86-87)
 };
 
-// One Drop::descend call given the five heights of the normal stencil (after the owed cascade).
+// water.h:70-117 given the five heights of the normal stencil (after the owed cascade).
 // inb: bit k of the 3x3 block (k = (dx+1)*3 + (dy+1)) set if that cell exists.
-// h2_at(nix, niy): fp32 height of an in-bounds cell (water.h:124), nearest cell, truncated.
-template <class H2>
-__device__ __forceinline__ StepResult descend_math(const float hc, const float hxm, const float hxp, const float hym,
-                                                   const float hyp, const unsigned inb, DropRegs& d, const float4 fld,
-                                                   const StepParams& P, const int size, H2&& h2_at) {
-  StepResult out;
+__device__ __forceinline__ MoveResult move_math(const float hc, const float hxm, const float hxp, const float hym,
+                                                const float hyp, const unsigned inb, DropRegs& d, const float4 fld,
+                                                const StepParams& P, const int size) {
+  MoveResult out;
   out.moved = false;
+  out.oob = false;
   out.dheight = 0.0f;
   out.t_d = out.t_mx = out.t_my = 0.0f;
+  out.cap = 1.0f;
+  out.effD = 0.0f;
 
   // cellpool.h:181-204.  height() of a missing cell is 0 (cellpool.h:433-437; the caller passes 0).
   // Each plane's cross product (cellpool.h:188,191,195,198) written out is (-+80*dh_x, 1, -+80*dh_y);
@@ -77,6 +86,7 @@ __device__ __forceinline__ StepResult descend_math(const float hc, const float h
 
   float effD = P.depositionRate * (1.0f - fld.w);  // water.h:86-87
   if (effD < 0.0f) effD = 0.0f;
+  out.effD = effD;
   {
     const float g = P.lod * P.gravity;  // water.h:95
     d.sx += (g * nx) / d.vol;
@@ -108,30 +118,31 @@ __device__ __forceinline__ StepResult descend_math(const float hc, const float h
   out.t_d = d.vol;
   out.t_mx = d.vol * d.sx;
   out.t_my = d.vol * d.sy;
+  out.cap = 1.0f + P.entrainment * shx_erff(0.4f * fld.x);  // water.h:127, cellpool.h:242-244
 
-  const int nix = (int)d.px, niy = (int)d.py;  // truncation, as ivec2(vec2)
-  // !(x > -1) also catches NaN, which the reference's cvttss2si maps to INT_MIN (out of bounds)
-  const bool oob = !(d.px > -1.0f) || !(d.py > -1.0f) || nix >= size || niy >= size;
-  float h2;
-  if (oob) h2 = (float)((double)hc - 0.002);  // water.h:121-122
-  else h2 = h2_at(nix, niy);                  // water.h:124
-  float c_eq = (1.0f + P.entrainment * shx_erff(0.4f * fld.x)) * (hc - h2);  // water.h:127-128
+  // truncation as ivec2(vec2); !(x > -1) also catches NaN, which the reference's cvttss2si maps to
+  // INT_MIN (out of bounds)
+  const int nix = (int)d.px, niy = (int)d.py;
+  out.oob = !(d.px > -1.0f) || !(d.py > -1.0f) || nix >= size || niy >= size;
+  return out;
+}
+
+// water.h:127-136: hc = old cell's height, h2 = new cell's height (or hc - 0.002 when out of bounds,
+// water.h:121-122, done by the caller).  Returns the fp32 amount to ADD to the old cell (-effD*cdiff).
+__device__ __forceinline__ float exchange_math(const float hc, const float h2, const float cap, const float effD, DropRegs& d,
+                                               const StepParams& P, float& carried) {
+  float c_eq = cap * (hc - h2);  // water.h:127-128
   if (c_eq < 0.0f) c_eq = 0.0f;
   const float cdiff = c_eq - d.sed;
   const float e = effD * cdiff;
-  d.sed += e;        // water.h:131
-  out.dheight = -e;  // water.h:132
+  d.sed += e;  // water.h:131
+  carried = d.sed;
   d.sed = (float)((double)d.sed / P.keep);  // water.h:135
   d.vol = (float)((double)d.vol * P.keep);  // water.h:136
-  if (oob) {  // water.h:139-142
-    d.vol = 0.0f;
-    d.flags = SHX_DROP_DONE_OOB;
-    return out;
-  }
-  d.age++;                      // water.h:153
-  d.flags |= SHX_DROP_CASCADE;  // water.h:151, executed at the start of the next phase
-  return out;
+  return -e;                                // water.h:132
 }
+
+__device__ __forceinline__ float oob_h2(const float hc) { return (float)((double)hc - 0.002); }  // water.h:121-122
 
 // World::cascade on a private fp32 3x3 block (sequential mode).  Block cell k = (dx+1)*3+(dy+1).
 __device__ __forceinline__ unsigned cascade_block_f32(float (&B)[9], const unsigned inb, const StepParams& P) {
