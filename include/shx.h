@@ -109,12 +109,15 @@ typedef struct {
   int row0, row1;      /* owned global rows [row0,row1) (x range); 0,0 = whole map */
   int halo;            /* halo rows kept on each side of a strip (>= 2); ignored for the whole map */
   size_t max_drops;    /* capacity of the drop buffers; 0 = maparea*1024 */
-  int block_threads;   /* 0 = choose; descend kernel CTA size */
-  int grid_blocks;     /* 0 = choose; descend kernel grid */
-  int variant;         /* 0 = 64-register build (1024 threads/SM), 1 = 128-register build (512 threads/SM) */
+  /* launch-shape overrides of the descend kernel (tuning / tests); all 0 = the library chooses by drop count.
+   * Results never depend on them: every shape is bit-identical. */
+  int block_threads;   /* CTA size */
+  int grid_blocks;     /* cap on the grid (smaller than the drop count => several launches in list order) */
+  int variant;         /* register budget: 0 = 64 (1024 threads/SM), 1 = 128 (512/SM), 2 = 72 (7x128/SM), 3 = 72 (2x448/SM) */
   int keep_tracks;     /* 0: erode's EMA pass also zeroes the *_track accumulators (the reset the reference
                           does at the START of the next call, world.h:56-61, hoisted into the same pass);
                           1: leave them readable after erode, at the cost of one more pass per call */
+  int coop;            /* 1 = warp-cooperative 3x3 gather (three lines per drop instead of nine lane accesses) */
 } shx_config;
 
 typedef struct shx_ctx shx_ctx;

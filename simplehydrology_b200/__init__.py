@@ -45,7 +45,7 @@ class Params(C.Structure):
 class Config(C.Structure):
     _fields_ = [("device", C.c_int), ("mode", C.c_int), ("row0", C.c_int), ("row1", C.c_int), ("halo", C.c_int),
                 ("max_drops", C.c_size_t), ("block_threads", C.c_int), ("grid_blocks", C.c_int), ("variant", C.c_int),
-                ("keep_tracks", C.c_int)]
+                ("keep_tracks", C.c_int), ("coop", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -136,14 +136,14 @@ class World:
     """Device-resident world; `erode(cycles)` is the reference's World::erode (world.h:54-88)."""
 
     def __init__(self, params=None, mapsize=1, mode=MODE_BATCHED, device=0, row0=0, row1=0, halo=2, max_drops=0,
-                 block_threads=0, grid_blocks=0, variant=0, keep_tracks=0):
+                 block_threads=0, grid_blocks=0, variant=0, keep_tracks=0, coop=0):
         self.L = lib()
         self.params = params if params is not None else default_params(mapsize)
         cfg = Config()
         self.L.shx_default_config(C.byref(cfg))
         cfg.device, cfg.mode, cfg.row0, cfg.row1, cfg.halo = device, mode, row0, row1, halo
         cfg.max_drops, cfg.block_threads, cfg.grid_blocks, cfg.variant = max_drops, block_threads, grid_blocks, variant
-        cfg.keep_tracks = keep_tracks
+        cfg.keep_tracks, cfg.coop = keep_tracks, coop
         self.cfg = cfg
         self.size = self.params.mapsize * self.params.tilesize
         self.ncells = self.size * self.size

@@ -11,6 +11,12 @@
 
 #include "shx_kernels.cuh"
 
+struct LaunchShape {
+  const void* kernel = nullptr;
+  int block = 0;
+  int cap_blocks = 0;  // co-resident CTAs (cooperative launch limit)
+};
+
 struct TimingSpan {
   int kind;  // 0 spawn, 1 descend, 2 ema
   cudaEvent_t e0, e1;
@@ -61,9 +67,8 @@ struct shx_ctx {
   uint64_t launches = 0;
   size_t last_n = 0;        // drops of the last run still sitting in d_drops
   bool tracks_clean = true; // all track accumulators are zero (world.h:56-61 already satisfied)
-  int cap_blocks_big = 0;   // co-resident CTAs of the multi-CTA instantiation at block_big
-  int block_big = 256;
-  const void* kernel_big = nullptr;
+  LaunchShape shape[2];     // multi-CTA launch shapes: [0] spread, [1] dense
+  bool forced_shape = false;
   bool timing = false;
   std::vector<TimingSpan> spans;
   bool strip_open = false;  // between shx_strip_erode_begin and _end
@@ -98,15 +103,19 @@ static size_t descend_smem(int block) { return (size_t)(9 + 16 + 16) * sizeof(in
 // 64 (1024 threads per SM); variant 1 allows 128 registers (512 threads per SM); variant 2 is
 // 7 CTAs of 128 threads per SM = 896 threads at 72 registers, just enough for the 886 drops per SM
 // of an 8192^2 cycle.
-#define KERNEL_SMALL descend_lockstep_kernel<1024, 1>
-static const void* big_kernel(int block, int variant) {
-  if (variant == 2) return (const void*)descend_lockstep_kernel<128, 7>;
-  if (variant == 1) return block <= 256 ? (const void*)descend_lockstep_kernel<256, 2> : (const void*)descend_lockstep_kernel<512, 1>;
-  if (block <= 128) return (const void*)descend_lockstep_kernel<128, 8>;
-  if (block <= 256) return (const void*)descend_lockstep_kernel<256, 4>;
-  if (block <= 512) return (const void*)descend_lockstep_kernel<512, 2>;
-  return (const void*)KERNEL_SMALL;
+// The last template argument selects the warp-cooperative block gather (see shx_kernels.cuh).
+#define KERNEL_SMALL descend_lockstep_kernel<1024, 1, false>
+#define PICK(T, B) (coop ? (const void*)descend_lockstep_kernel<T, B, true> : (const void*)descend_lockstep_kernel<T, B, false>)
+static const void* big_kernel(int block, int variant, bool coop) {
+  if (variant == 2) return PICK(128, 7);
+  if (variant == 3) return PICK(448, 2);  // same 896 threads/SM, 296 CTAs
+  if (variant == 1) return block <= 256 ? PICK(256, 2) : PICK(512, 1);
+  if (block <= 128) return PICK(128, 8);
+  if (block <= 256) return PICK(256, 4);
+  if (block <= 512) return PICK(512, 2);
+  return PICK(1024, 1);
 }
+#undef PICK
 
 extern "C" {
 
@@ -224,19 +233,39 @@ int shx_create(shx_ctx** out, const shx_params* p, const shx_config* cfg_in) {
   cudaMemset(c->d_stats, 0, ST_COUNT * 8);
   cudaMemset(c->d_flags, 0, 4 * sizeof(int));
 
-  c->block_big = cfg.block_threads > 0 ? std::min(1024, (cfg.block_threads + 31) / 32 * 32) : 256;
-  if (cfg.variant == 1) c->block_big = std::min(c->block_big, 512);
-  if (cfg.variant == 2) c->block_big = std::min(c->block_big, 128);
-  c->kernel_big = big_kernel(c->block_big, cfg.variant);
-  int nb = 0;
-  if (cudaFuncSetAttribute(KERNEL_SMALL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)descend_smem(1024)) != cudaSuccess ||
-      cudaFuncSetAttribute(c->kernel_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)descend_smem(c->block_big)) != cudaSuccess ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, c->kernel_big, c->block_big, descend_smem(c->block_big)) != cudaSuccess ||
-      nb < 1) {
+  // Launch shapes of the multi-CTA descend kernel, both with the cooperative gather.  [0] "spread":
+  // CTAs of 64 so that a few thousand drops still cover all SMs (latency-bound regime); [1] "dense":
+  // 2 x 448 threads per SM at 72 registers (throughput regime, >= ~256 drops per SM).  An explicit
+  // block_threads / variant / coop / grid_blocks in the config forces one shape for both.
+  const bool forced = cfg.block_threads > 0 || cfg.variant > 0 || cfg.coop > 0 || cfg.grid_blocks > 0;
+  for (int i = 0; i < 2; i++) {
+    LaunchShape& ls = c->shape[i];
+    if (forced) {
+      ls.block = cfg.block_threads > 0 ? std::min(1024, (cfg.block_threads + 31) / 32 * 32) : 256;
+      if (cfg.variant == 1) ls.block = std::min(ls.block, 512);
+      if (cfg.variant == 2) ls.block = std::min(ls.block, 128);
+      if (cfg.variant == 3) ls.block = 448;
+      ls.kernel = big_kernel(ls.block, cfg.variant, cfg.coop == 1);
+    } else if (i == 0) {
+      ls.block = 64;
+      ls.kernel = big_kernel(64, 2, true);
+    } else {
+      ls.block = 448;
+      ls.kernel = big_kernel(448, 3, true);
+    }
+    int nb = 0;
+    if (cudaFuncSetAttribute(ls.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)descend_smem(ls.block)) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls.kernel, ls.block, descend_smem(ls.block)) != cudaSuccess || nb < 1) {
+      shx_destroy(c);
+      return fail(SHX_ERR_CUDA, "descend kernel does not fit on this device");
+    }
+    ls.cap_blocks = nb * c->sm_count;
+  }
+  c->forced_shape = forced;
+  if (cudaFuncSetAttribute(KERNEL_SMALL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)descend_smem(1024)) != cudaSuccess) {
     shx_destroy(c);
     return fail(SHX_ERR_CUDA, "descend kernel does not fit on this device");
   }
-  c->cap_blocks_big = nb * c->sm_count;
   if (cudaDeviceSynchronize() != cudaSuccess) {
     shx_destroy(c);
     return fail(SHX_ERR_CUDA, "context initialisation failed");
@@ -479,20 +508,22 @@ static int run_device_drops(shx_ctx* c, size_t n, bool trace) {
     CU(cudaMemsetAsync(c->d_bar, 0, sizeof(GridBar), c->stream));
     void* args[] = {&a};
     size_t take;
-    const bool force_grid = c->cfg.grid_blocks > 0 || c->cfg.block_threads > 0;
-    if (left <= 1024 && !force_grid) {
+    if (left <= 64 && !c->forced_shape) {
+      // a handful of drops: one CTA, the per-phase barrier is a plain __syncthreads
       take = left;
       a.ndrops = (unsigned)take;
       const int block = (int)((take + 31) / 32 * 32);
       CU(cudaLaunchCooperativeKernel((void*)KERNEL_SMALL, dim3(1), dim3(block), args, descend_smem(block), c->stream));
     } else {
-      const int block = c->block_big;
-      int cap = c->cap_blocks_big;
+      // dense shape once the spread shape would put more than ~4 CTAs of 64 on every SM
+      const LaunchShape& ls = c->shape[(left > (size_t)c->sm_count * 256) ? 1 : 0];
+      const int block = ls.block;
+      int cap = ls.cap_blocks;
       if (c->cfg.grid_blocks > 0) cap = std::min(cap, c->cfg.grid_blocks);
       take = std::min(left, (size_t)cap * block);
       a.ndrops = (unsigned)take;
       const int grid = (int)((take + block - 1) / block);
-      CU(cudaLaunchCooperativeKernel(c->kernel_big, dim3(grid), dim3(block), args, descend_smem(block), c->stream));
+      CU(cudaLaunchCooperativeKernel(ls.kernel, dim3(grid), dim3(block), args, descend_smem(block), c->stream));
     }
     c->launches++;
     done += take;
@@ -837,6 +868,17 @@ int shx_strip_erode_end(shx_ctx* c) {
 }
 
 #ifdef SHX_PHASE_TIMING
+int shx_debug_starts(unsigned long long* ns8192) {
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpyFromSymbol(ns8192, g_start, 8192 * sizeof(unsigned long long)));
+  return SHX_OK;
+}
+int shx_debug_arrivals(unsigned long long* ns8192, unsigned* sm8192) {
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpyFromSymbol(ns8192, g_arrival, 8192 * sizeof(unsigned long long)));
+  CU(cudaMemcpyFromSymbol(sm8192, g_arrival_sm, 8192 * sizeof(unsigned)));
+  return SHX_OK;
+}
 int shx_debug_set_exp(unsigned flags) {
   CU(cudaMemcpyToSymbol(g_exp, &flags, sizeof flags));
   return SHX_OK;

@@ -34,10 +34,11 @@ enum StatIndex {
 static_assert(sizeof(shx_stats) == ST_COUNT * 8, "shx_stats layout");
 
 struct GridBar {
-  unsigned count;
-  unsigned active[4];
+  // one 64-bit word per phase parity: low half counts CTA arrivals, high half sums "drops still
+  // active"; both monotonically increasing over the launch (zeroed by the host before it)
+  unsigned long long word[2];
   unsigned max_steps;  // longest drop of this launch == number of phases that had a live drop
-  unsigned pad[2];
+  unsigned pad[3];
 };
 
 struct DescendArgs {
@@ -56,30 +57,48 @@ __device__ __forceinline__ void stat_add(unsigned long long* stats, int i, unsig
   atomicAdd(stats + i, v);
 }
 
+#ifdef SHX_PHASE_TIMING
+// development aid (tools/phase_timing.py, tools/arrival_hist.py): cycle stamps of thread 0 / block 0
+// per phase section, per-warp barrier arrival times of one phase, experiment switches
+__device__ unsigned long long g_phase_timing[8];
+__device__ unsigned long long g_arrival[8192];
+__device__ unsigned long long g_start[8192];
+__device__ unsigned g_arrival_sm[8192];
+__device__ unsigned g_exp;  // 1 no track atomics, 2 no height atomics, 4 no cascade, 8 poll back-off
+#define SHX_EXP(bit) (g_exp & (bit))
+#define SHX_T(i) do { if (gid == 0) tstamp[i] = clock64(); } while (0)
+#else
+#define SHX_T(i) do { } while (0)
+#define SHX_EXP(bit) 0
+#endif
+
 // ---------------------------------------------------------------------------------------------
-// Grid-wide barrier that also sums a per-CTA count (drops still active).  One arrival per CTA on
-// a monotonically increasing counter in L2; `active` is a 4-slot ring so that the sum of phase p
-// can be read after the barrier while phase p+1 is already accumulating.  The kernel is launched
-// cooperatively (all CTAs co-resident).  Returns the grid-wide sum.
-__device__ __forceinline__ unsigned grid_barrier_sum(GridBar* bar, unsigned phase, unsigned block_sum, unsigned* s_total) {
+// Grid-wide barrier that also sums a per-CTA count (drops still active).  One 64-bit RED per CTA:
+// arrival count in the low half, the count to be summed in the high half, on the word of this
+// phase's parity; thread 0 polls that word, so the arrival count and the sum come from ONE load.
+// Phase p+2 reuses the word of phase p, which is safe because nobody can arrive at barrier p+2
+// before everybody has left barrier p.  prev_hi[] remembers the high half after the word's previous
+// use (identical in every CTA).  The kernel is launched cooperatively (all CTAs co-resident).
+__device__ __forceinline__ unsigned grid_barrier_sum(GridBar* bar, unsigned phase, unsigned block_sum, unsigned* s_total,
+                                                     unsigned& prev_hi0, unsigned& prev_hi1) {
   // The caller has just passed a __syncthreads-class barrier (block_sum comes from
   // __syncthreads_count), so every RED of this CTA for this phase was issued before thread 0's fence.
   if (gridDim.x == 1) return block_sum;
   if (threadIdx.x == 0) {
-    const unsigned slot = phase & 3u;
-    if (block_sum) atomicAdd(&bar->active[slot], block_sum);
-    __threadfence();
-    atomicAdd(&bar->count, 1u);
-    const unsigned target = (phase + 1u) * gridDim.x;
-    unsigned seen;
+    unsigned long long* w = &bar->word[phase & 1u];
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");  // release: this CTA's REDs before the arrival
+    atomicAdd(w, ((unsigned long long)block_sum << 32) | 1ull);
+    const unsigned target = (phase / 2u + 1u) * gridDim.x;
+    unsigned long long seen;
     do {  // relaxed polling (an acquire load per iteration would invalidate L1 every time)
-      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(&bar->count) : "memory");
-    } while (seen < target);
-    __threadfence();
-    unsigned total;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(total) : "l"(&bar->active[slot]) : "memory");
-    if (blockIdx.x == 0) bar->active[(phase + 2u) & 3u] = 0u;
-    *s_total = total;
+      if (SHX_EXP(8)) __nanosleep(200);
+      asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(w) : "memory");
+    } while ((int)((unsigned)seen - target) < 0);
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");  // acquire: the other CTAs' REDs before our reads
+    const unsigned hi = (unsigned)(seen >> 32);
+    *s_total = hi - ((phase & 1u) ? prev_hi1 : prev_hi0);
+    if (phase & 1u) prev_hi1 = hi;
+    else prev_hi0 = hi;
   }
   __syncthreads();
   return *s_total;
@@ -94,16 +113,6 @@ __device__ __forceinline__ float ord2f(unsigned u) {
   return __uint_as_float(u ^ (((u >> 31) - 1u) | 0x80000000u));
 }
 
-#ifdef SHX_PHASE_TIMING
-// development aid: cycle stamps of thread 0 / block 0 accumulated per phase section
-__device__ unsigned long long g_phase_timing[8];
-__device__ unsigned g_exp;  // experiment switches: 1 no track atomics, 2 no height atomics, 4 no cascade
-#define SHX_EXP(bit) (g_exp & (bit))
-#define SHX_T(i) do { if (gid == 0) tstamp[i] = clock64(); } while (0)
-#else
-#define SHX_T(i) do { } while (0)
-#define SHX_EXP(bit) 0
-#endif
 
 // ---------------------------------------------------------------------------------------------
 // K3: batched lock-step descend.  One thread per drop, drop state in registers, the 3x3 block of
@@ -118,20 +127,31 @@ __device__ unsigned g_exp;  // experiment switches: 1 no track atomics, 2 no hei
 // order in which drops are scheduled and are run-to-run identical.
 //
 // Work of one phase for one drop (see shx_step.cuh for the split of Drop::descend):
-//   [exchange_math of the previous call, against the centre of the block just loaded]
-//   [World::cascade owed by the previous call]   move_math of this call   track REDs
-// A call that leaves the map, or the strip, does its exchange immediately.
+//   [World::cascade owed by the previous call]   move_math   track REDs   exchange_math
 //
-// Shared memory per thread: s_B[9] block heights, s_D[2][8] neighbour deltas of this / the previous
-// phase, s_S[8] (height, index) pairs in cascade order.
-template <int kMaxThreads, int kMinBlocks>
+// kCoop selects how the 3x3 block is gathered.  With one load per lane and cell, every lane of a
+// load instruction touches its own 128-byte line and the SM's L1TEX pipe replays the instruction
+// once per line (~2 cycles each): at 28 resident warps per SM that replay time, not DRAM or L2
+// bandwidth, bounds the phase.  The cooperative gather lets nine lanes fetch the nine cells of ONE
+// drop (three drops per instruction): three lines per drop instead of nine lane-wavefronts; the
+// values travel through shared memory to the lane that owns the drop.
+//
+// Shared memory per thread: s_B[9] block heights (thread-major, stride 9: conflict-free both for
+// the owner's sequential reads and for the cooperative stores), s_D[2][8] neighbour deltas of this
+// / the previous phase, s_S[8] (height, index) pairs in cascade order.
+template <int kMaxThreads, int kMinBlocks, bool kCoop>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kernel(const __grid_constant__ DescendArgs a) {
   extern __shared__ int32_t s_mem[];
   __shared__ unsigned s_total;
   const int tid = threadIdx.x, nt = blockDim.x;
-  int32_t* s_B = s_mem + tid;                                   // s_B[k*nt]
+  int32_t* s_B = s_mem + tid * 9;                               // s_B[k]
   int32_t* s_D = s_mem + 9 * nt + tid;                          // s_D[(buf*8 + j)*nt]
   uint2* s_S = reinterpret_cast<uint2*>(s_mem + 25 * nt) + tid; // s_S[r*nt]
+  // cooperative gather: lane -> (which of 3 drops of a group, which of its 9 cells)
+  const int lane = tid & 31;
+  const int co_k = lane % 9, co_sub = lane / 9;
+  const int co_off = (co_k / 3 - 1) * a.m.size + (co_k % 3 - 1);
+  int32_t* const s_Bw = s_mem + (tid - lane) * 9;               // first drop of this warp
   const unsigned gid = blockIdx.x * nt + tid;
   const int size = a.m.size;
   int* const H = reinterpret_cast<int*>(a.m.hq);
@@ -151,6 +171,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
   int dC_prev = 0;          // centre
   unsigned dmask_prev = 0;  // neighbours (values in s_D)
   int pidx = 0;
+  unsigned bar_hi0 = 0, bar_hi1 = 0;  // grid barrier bookkeeping (thread 0)
   unsigned steps = 0, transfers = 0;
   long long fx_eroded = 0, fx_inflation = 0;
   int tn = 0;
@@ -171,6 +192,13 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
     const int rpar = (int)(phase & 1u), wpar = rpar ^ 1;
     const int cur = rpar * 8, prev = wpar * 8;
     SHX_T(0);
+#ifdef SHX_PHASE_TIMING
+    if (phase == 100u && (tid & 31) == 0 && (gid >> 5) < 8192u) {
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+      g_start[gid >> 5] = ns;
+    }
+#endif
 
     // Issue this phase's gathers first (they only touch the read plane), then the catch-up adds of
     // the previous phase (write plane): the loads do not queue behind the atomics' round trip.
@@ -182,7 +210,27 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
                          ((xp & ym) << 6) | (xp << 7) | ((xp & yp) << 8);
     int v[9];
     float4 fld = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    if (alive) {
+    if (kCoop) {
+      // 11 groups of 3 drops; lane (sub, k) loads cell k of drop 3g+sub of this warp into its s_B row
+      const unsigned meta = alive ? (inb | 0x200u) : 0u;
+      if (__any_sync(0xffffffffu, alive)) {
+        int got[11];
+#pragma unroll
+        for (int g = 0; g < 11; g++) {
+          const int src = g * 3 + co_sub;
+          const int c = __shfl_sync(0xffffffffu, cidx, src & 31);
+          const unsigned m = __shfl_sync(0xffffffffu, meta, src & 31);
+          const bool ok = co_sub < 3 && src < 32 && ((m >> co_k) & 1u) && (m & 0x200u);
+          got[g] = ok ? __ldcg(H + 2 * (c + co_off) + rpar) : 0;
+        }
+        if (alive) fld = __ldg(reinterpret_cast<const float4*>(a.m.rec + cidx));
+#pragma unroll
+        for (int g = 0; g < 11; g++) {
+          const int src = g * 3 + co_sub;
+          if (co_sub < 3 && src < 32) s_Bw[src * 9 + co_k] = got[g];
+        }
+      }
+    } else if (alive) {
       const int* c = H + 2 * cidx + rpar;
 #pragma unroll
       for (int k = 0; k < 9; k++) {
@@ -206,10 +254,15 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
       dmask_prev = 0;
     }
 
+    if (kCoop) __syncwarp();  // the block rows written by the other lanes of the warp are complete
+
     if (alive) {
       steps++;
 #pragma unroll
-      for (int k = 0; k < 9; k++) s_B[k * nt] = v[k];
+      for (int k = 0; k < 9; k++) {
+        if (kCoop) v[k] = s_B[k];
+        else s_B[k] = v[k];
+      }
       int Bc = v[4];
       unsigned dmask = 0;
       SHX_T(1);
@@ -266,7 +319,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
                 const int k = (int)(j + (j >> 2));
                 const int kx = (k * 11) >> 5;
                 const int off = kx * size - size + (k - 3 * kx) - 1;
-                s_B[k * nt] += s;
+                s_B[k] += s;
                 s_D[(cur + (int)j) * nt] = s;
                 dmask |= 1u << j;
                 if (!SHX_EXP(2)) atomicAdd(H + 2 * (cidx + off) + wpar, s);
@@ -274,14 +327,14 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
               }
             }
           }
-          s_B[4 * nt] = Bc;
+          s_B[4] = Bc;
         }
       }
       SHX_T(2);
 
       const float hc = h_to_float(Bc);
-      const float hxm = xm ? h_to_float(s_B[1 * nt]) : 0.0f, hxp = xp ? h_to_float(s_B[7 * nt]) : 0.0f;
-      const float hym = ym ? h_to_float(s_B[3 * nt]) : 0.0f, hyp = yp ? h_to_float(s_B[5 * nt]) : 0.0f;
+      const float hxm = xm ? h_to_float(s_B[1]) : 0.0f, hxp = xp ? h_to_float(s_B[7]) : 0.0f;
+      const float hym = ym ? h_to_float(s_B[3]) : 0.0f, hyp = yp ? h_to_float(s_B[5]) : 0.0f;
       const MoveResult mv = move_math(hc, hxm, hxp, hym, hyp, inb, d, fld, a.P, size);
       int dC = Bc - v[4];
       SHX_T(3);
@@ -295,6 +348,16 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
         stat_add(a.stats, ST_FX_SED_DEPOSITED, (unsigned long long)l_quantize(d.sed));
         SHX_TRACE_ROW();
       } else {
+        // water.h:124: the new cell (nearest, truncated) may lie outside the block: issue that one
+        // dependent gather first and do the erf and the track adds while it is in flight
+        const int nix = (int)d.px, niy = (int)d.py;
+        int hv = 0;
+        if (!mv.oob) {
+          const int ddx = nix - ix, ddy = niy - iy;
+          if (ddx >= -1 && ddx <= 1 && ddy >= -1 && ddy <= 1) hv = s_B[(ddx + 1) * 3 + (ddy + 1)];
+          else hv = __ldcg(H + 2 * ((nix - a.m.xlo) * size + niy) + rpar);
+        }
+        const float cap = 1.0f + a.P.entrainment * shx_erff(0.4f * fld.x);  // water.h:127, cellpool.h:242-244
         if (!SHX_EXP(1)) {  // water.h:115-117.  discharge (>= 0, low word) and momentum-x (high word)
           // go out as ONE 64-bit add: the low word cannot carry while the Q13.18 range check holds
           CellRec* rec = a.m.rec + cidx;
@@ -303,19 +366,9 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
           atomicAdd(reinterpret_cast<unsigned long long*>(&rec->track_d), packed);
           atomicAdd(&rec->track_my, t_quantize(mv.t_my));
         }
-        const int nix = (int)d.px, niy = (int)d.py;
-        float h2;
-        if (mv.oob) {
-          h2 = oob_h2(hc);  // water.h:121-122
-        } else {              // water.h:124: nearest cell, truncated; it may lie outside the block
-          const int ddx = nix - ix, ddy = niy - iy;
-          int hv;
-          if (ddx >= -1 && ddx <= 1 && ddy >= -1 && ddy <= 1) hv = s_B[((ddx + 1) * 3 + (ddy + 1)) * nt];
-          else hv = __ldcg(H + 2 * ((nix - a.m.xlo) * size + niy) + rpar);
-          h2 = h_to_float(hv);
-        }
+        const float h2 = mv.oob ? oob_h2(hc) : h_to_float(hv);  // water.h:121-124
         float carried;
-        const float dh = exchange_math(hc, h2, mv.cap, mv.effD, d, a.P, carried);  // water.h:127-136
+        const float dh = exchange_math(hc, h2, cap, mv.effD, d, a.P, carried);  // water.h:127-136
         const int q = h_quantize(dh);
         dC += q;
         fx_eroded -= (long long)q;
@@ -347,9 +400,19 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
     }
 
     SHX_T(4);
+#ifdef SHX_PHASE_TIMING
+    if (phase == 100u && (tid & 31) == 0) {  // per-warp arrival times of one phase (ns, global timer)
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      const unsigned w = gid >> 5;
+      if (w < 8192u) { g_arrival[w] = ns; g_arrival_sm[w] = smid; }
+    }
+#endif
     const unsigned block_sum = (unsigned)__syncthreads_count(alive || (dC_prev | (int)dmask_prev));
     SHX_T(5);
-    const unsigned total = grid_barrier_sum(a.bar, phase, block_sum, &s_total);
+    const unsigned total = grid_barrier_sum(a.bar, phase, block_sum, &s_total, bar_hi0, bar_hi1);
     SHX_T(6);
 #ifdef SHX_PHASE_TIMING
     if (gid == 0 && alive) {
@@ -454,7 +517,8 @@ __global__ void descend_sequential_kernel(const SequentialArgs a) {
           }
         }
         float carried;
-        B[4] = B[4] + exchange_math(B[4], h2, mv.cap, mv.effD, d, a.P, carried);  // water.h:127-136
+        const float cap = 1.0f + a.P.entrainment * shx_erff(0.4f * fld.x);  // water.h:127, cellpool.h:242-244
+        B[4] = B[4] + exchange_math(B[4], h2, cap, mv.effD, d, a.P, carried);  // water.h:127-136
         fx_inflation += l_quantize(d.sed) - l_quantize(carried);
         if (mv.oob) {  // water.h:139-142
           d.vol = 0.0f;

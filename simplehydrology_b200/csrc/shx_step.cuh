@@ -11,11 +11,10 @@
 //   exchange_math  water.h:120-136  sediment exchange with the OLD cell against the NEW cell's height, evaporation
 // followed by water.h:139-154 (out-of-bounds stop, cascade at the new cell, age++).
 //
-// Sequential mode runs them back to back like the reference.  The batched mode defers exchange_math
-// of step k to the start of phase k+1: the new cell's height it needs (water.h:124) is then the
-// centre of the block that phase loads anyway, which removes the only dependent second gather of a
-// step.  For one drop the order of effects is unchanged: exchange(k) -> cascade at the new cell ->
-// move(k+1), exactly water.h:127-154 followed by the next call.
+// Both modes run them back to back like the reference.  (Deferring exchange_math of step k to phase
+// k+1 -- where the new cell is the centre of the block loaded anyway -- would remove the one dependent
+// gather of a step; it was tried and rejected: the erosion of a cell then becomes visible to the
+// other drops one phase later, and dense flows (thousands of drops per tile) go unstable.)
 #pragma once
 #include "../../include/shx.h"
 #include "shx_math.cuh"
@@ -43,7 +42,6 @@ struct MoveResult {
   bool oob;               // new position outside the map (water.h:121,139)
   float dheight;          // termination only: fp32 amount to ADD to the centre cell
   float t_d, t_mx, t_my;  // track deposits at the old cell (water.h:115-117)
-  float cap;              // 1 + entrainment*erf(0.4*discharge) of the old cell (water.h:127)
   float effD;             // depositionRate*(1-rootdensity), clamped (water.h:86-87)
 };
 
@@ -57,7 +55,6 @@ __device__ __forceinline__ MoveResult move_math(const float hc, const float hxm,
   out.oob = false;
   out.dheight = 0.0f;
   out.t_d = out.t_mx = out.t_my = 0.0f;
-  out.cap = 1.0f;
   out.effD = 0.0f;
 
   // cellpool.h:181-204.  height() of a missing cell is 0 (cellpool.h:433-437; the caller passes 0).
@@ -118,7 +115,6 @@ __device__ __forceinline__ MoveResult move_math(const float hc, const float hxm,
   out.t_d = d.vol;
   out.t_mx = d.vol * d.sx;
   out.t_my = d.vol * d.sy;
-  out.cap = 1.0f + P.entrainment * shx_erff(0.4f * fld.x);  // water.h:127, cellpool.h:242-244
 
   // truncation as ivec2(vec2); !(x > -1) also catches NaN, which the reference's cvttss2si maps to
   // INT_MIN (out of bounds)
@@ -128,7 +124,8 @@ __device__ __forceinline__ MoveResult move_math(const float hc, const float hxm,
 }
 
 // water.h:127-136: hc = old cell's height, h2 = new cell's height (or hc - 0.002 when out of bounds,
-// water.h:121-122, done by the caller).  Returns the fp32 amount to ADD to the old cell (-effD*cdiff).
+// water.h:121-122, done by the caller), cap = 1 + entrainment*erf(0.4*discharge) of the old cell
+// (water.h:127, cellpool.h:242-244).  Returns the fp32 amount to ADD to the old cell (-effD*cdiff).
 __device__ __forceinline__ float exchange_math(const float hc, const float h2, const float cap, const float effD, DropRegs& d,
                                                const StepParams& P, float& carried) {
   float c_eq = cap * (hc - h2);  // water.h:127-128

@@ -10,8 +10,8 @@ sys.path.insert(0, ROOT)
 import simplehydrology_b200 as shx  # noqa: E402
 
 
-def run(ms, block, variant, grid, cycles=512, warm=4, n=6):
-    W = shx.World(mapsize=ms, block_threads=block, variant=variant, grid_blocks=grid)
+def run(ms, block, variant, grid, coop=0, cycles=512, warm=4, n=6):
+    W = shx.World(mapsize=ms, block_threads=block, variant=variant, grid_blocks=grid, coop=coop)
     W.set_stream(torch.cuda.current_stream().cuda_stream)
     W.synth_terrain(1)
     for _ in range(warm):
@@ -26,7 +26,7 @@ def run(ms, block, variant, grid, cycles=512, warm=4, n=6):
     t = e0.elapsed_time(e1) / n
     st = W.erode(cycles, 1)
     W.close()
-    print(f"mapsize {ms} block {block} variant {variant} grid {grid}: {t:.3f} ms/cycle  {t*1e3/max(st.phases,1):.2f} us/phase  "
+    print(f"mapsize {ms} block {block} variant {variant} grid {grid} coop {coop}: {t:.3f} ms/cycle  {t*1e3/max(st.phases,1):.2f} us/phase  "
           f"{st.steps/(t*1e-3)/1e9:.3f} Gsteps/s  launches {st.launches}", flush=True)
 
 
@@ -34,5 +34,5 @@ if __name__ == "__main__":
     ms = int(sys.argv[1])
     cfgs = sys.argv[2:] or ["256:0:0"]
     for c in cfgs:
-        b, v, g = (int(x) for x in c.split(":"))
-        run(ms, b, v, g)
+        b, v, g, co = (int(x) for x in (c.split(":") + ["0"])[:4])
+        run(ms, b, v, g, co)
