@@ -162,10 +162,17 @@ def run_cuda(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    strip = strips.GpuStrip(MAPSIZE, rank, world, local)
+    peer = world > 1 and args.multi == "peer"
+    if peer:
+        # one world over all GPUs: peer-mapped strips, the kernel itself crosses NVLink
+        strip = strips.PeerWorld(MAPSIZE, rank, world, local)
+        strip.W.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        ex = None
+    else:
+        strip = strips.GpuStrip(MAPSIZE, rank, world, local)
+        ex = strips.StripExchange(strip, rank, world)
     W = strip.W
     W.synth_terrain(SEED)
-    ex = strips.StripExchange(strip, rank, world)
     names = [n for n, _ in shx.Stats._fields_]
 
     def barrier():
@@ -173,9 +180,11 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    barrier()  # every strip holds its terrain before anybody's kernel reads across a border
+
     def one_step():
         """one erosion cycle on the device-resident world; returns this rank's counters"""
-        if world == 1:
+        if world == 1 or peer:
             W.erode_async(CYCLES, SEED)
         else:
             ex.erode(CYCLES, SEED)
@@ -200,7 +209,7 @@ def run_cuda(args):
         st = one_step()
         for n in names:
             acc[n] += int(getattr(st, n))
-        rounds += ex.rounds if world > 1 else 0
+        rounds += ex.rounds if ex is not None and world > 1 else 0
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -237,7 +246,7 @@ def run_cuda(args):
                 "config": {"workload": "8192x8192 world (mapsize 16, BASELINE configs[3]); one step = one erode(512) cycle: 131072 drops, "
                                        "lock-step batched descend + cascade, EMA",
                            "map": "8192x8192", "drops_per_cycle": MAPSIZE * MAPSIZE * CYCLES,
-                           "parallelism": f"row strips x{world}" if world > 1 else "single GPU",
+                           "parallelism": (f"row strips x{world}, peer-mapped over NVLink, one cross-GPU barrier per phase" if peer else f"row strips x{world}, exchange rounds") if world > 1 else "single GPU",
                            "l2": "inputs larger than L2 (2.7 GB of map state vs 126 MB): no flush needed", "seed": SEED},
                 "cycles_per_s": args.steps / (ms * 1e-3),
                 "mean_steps_per_drop": psteps / max(total["spawned"], 1),
@@ -251,7 +260,8 @@ def run_cuda(args):
                                             "algorithmic_bytes_per_cell": BYTES_PER_CELL_EMA}},
                 "clocks": clocks}
         if world > 1:
-            line["exchange_rounds_per_cycle"] = rounds / max(args.steps, 1)
+            if not peer:
+                line["exchange_rounds_per_cycle"] = rounds / max(args.steps, 1)
 
     # ---- e2e: the calls the host adaptor makes, with host buffers; with strips every rank downloads
     # its own rows into its own (whole-map sized, as the reference's) pool
@@ -326,6 +336,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--e2e-mask", default="all", choices=["all", "hdm"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--multi", default="peer", choices=["peer", "strips"], help="N > 1: peer-mapped lock step (default) or exchange-round strips")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

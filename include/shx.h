@@ -38,7 +38,8 @@ enum {
   SHX_ERR_RANGE = -3,     /* a height does not fit the Q5.26 fixed point (|h| >= 32) */
   SHX_ERR_MODE = -4,      /* call not available in this context's mode */
   SHX_ERR_CAPACITY = -5,  /* more drops than the context was sized for */
-  SHX_ERR_NOMEM = -6
+  SHX_ERR_NOMEM = -6,
+  SHX_ERR_PEER = -7       /* peer mode: not attached, or a peer GPU did not reach a phase barrier in time */
 };
 
 /* == quad::cell, cellpool.h:207-220: 8 x f32 = 32 B in this order.  Host buffers are
@@ -118,7 +119,21 @@ typedef struct {
                           does at the START of the next call, world.h:56-61, hoisted into the same pass);
                           1: leave them readable after erode, at the cost of one more pass per call */
   int coop;            /* 1 = warp-cooperative 3x3 gather (three lines per drop instead of nine lane accesses) */
+  /* peer mode: ONE world spread over peer_world GPUs of a box, one process (context) per GPU.  This
+   * context owns rows [rank*size/world, (rank+1)*size/world) -- row0/row1/halo are ignored -- and,
+   * after shx_peer_attach, reads and adds into the other ranks' strips over NVLink from inside the
+   * descend kernel; the per-phase barrier spans all GPUs.  Same schedule as one GPU => same result.
+   * Every rank must make the same sequence of erode / run calls.  size/world must be a power of two
+   * and a multiple of tilesize. */
+  int peer_rank, peer_world;
 } shx_config;
+
+/* CUDA IPC handles of one rank's strip (opaque bytes; gather them from all ranks with the caller's
+ * own transport, e.g. torch.distributed.all_gather_object, and hand the array to shx_peer_attach) */
+typedef struct {
+  unsigned char hq[64], rec[64], inbox[64]; /* cudaIpcMemHandle_t of the allocations holding the buffers */
+  uint64_t off_hq, off_rec, off_inbox;      /* byte offsets of the buffers inside those allocations */
+} shx_peer_handles;
 
 typedef struct shx_ctx shx_ctx;
 
@@ -213,6 +228,10 @@ int shx_strip_run_device_drops(shx_ctx* c, const shx_drop* dev_drops, size_t n, 
  * stats accumulate from begin to end (shx_read_stats after end). */
 int shx_strip_erode_begin(shx_ctx* c, int cycles, uint64_t seed);
 int shx_strip_erode_end(shx_ctx* c);
+
+/* ---- peer mode (shx_config.peer_world > 1): export this rank's strip, map everybody's */
+int shx_peer_export(shx_ctx* c, shx_peer_handles* out);
+int shx_peer_attach(shx_ctx* c, const shx_peer_handles* all_ranks /* peer_world entries, index = rank */);
 
 #ifdef __cplusplus
 }

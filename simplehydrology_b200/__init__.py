@@ -45,7 +45,12 @@ class Params(C.Structure):
 class Config(C.Structure):
     _fields_ = [("device", C.c_int), ("mode", C.c_int), ("row0", C.c_int), ("row1", C.c_int), ("halo", C.c_int),
                 ("max_drops", C.c_size_t), ("block_threads", C.c_int), ("grid_blocks", C.c_int), ("variant", C.c_int),
-                ("keep_tracks", C.c_int), ("coop", C.c_int)]
+                ("keep_tracks", C.c_int), ("coop", C.c_int), ("peer_rank", C.c_int), ("peer_world", C.c_int)]
+
+
+class PeerHandles(C.Structure):
+    _fields_ = [("hq", C.c_ubyte * 64), ("rec", C.c_ubyte * 64), ("inbox", C.c_ubyte * 64),
+                ("off_hq", C.c_uint64), ("off_rec", C.c_uint64), ("off_inbox", C.c_uint64)]
 
 
 class Stats(C.Structure):
@@ -118,6 +123,8 @@ def lib():
     L.shx_strip_run_device_drops.argtypes = [vp, vp, sz, C.POINTER(Stats)]
     L.shx_strip_erode_begin.argtypes = [vp, C.c_int, u64]
     L.shx_strip_erode_end.argtypes = [vp]
+    L.shx_peer_export.argtypes = [vp, C.POINTER(PeerHandles)]
+    L.shx_peer_attach.argtypes = [vp, C.POINTER(PeerHandles)]
     _lib = L
     return L
 
@@ -136,7 +143,7 @@ class World:
     """Device-resident world; `erode(cycles)` is the reference's World::erode (world.h:54-88)."""
 
     def __init__(self, params=None, mapsize=1, mode=MODE_BATCHED, device=0, row0=0, row1=0, halo=2, max_drops=0,
-                 block_threads=0, grid_blocks=0, variant=0, keep_tracks=0, coop=0):
+                 block_threads=0, grid_blocks=0, variant=0, keep_tracks=0, coop=0, peer_rank=0, peer_world=0):
         self.L = lib()
         self.params = params if params is not None else default_params(mapsize)
         cfg = Config()
@@ -144,6 +151,7 @@ class World:
         cfg.device, cfg.mode, cfg.row0, cfg.row1, cfg.halo = device, mode, row0, row1, halo
         cfg.max_drops, cfg.block_threads, cfg.grid_blocks, cfg.variant = max_drops, block_threads, grid_blocks, variant
         cfg.keep_tracks, cfg.coop = keep_tracks, coop
+        cfg.peer_rank, cfg.peer_world = peer_rank, peer_world
         self.cfg = cfg
         self.size = self.params.mapsize * self.params.tilesize
         self.ncells = self.size * self.size
@@ -303,6 +311,19 @@ class World:
         a, b = C.c_int(), C.c_int()
         self._check(self.L.shx_strip_pack_migrants(self._h, lo, hi, cap, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    # -- peer mode: one world over the GPUs of a box
+    def peer_export(self):
+        h = PeerHandles()
+        self._check(self.L.shx_peer_export(self._h, C.byref(h)))
+        return bytes(h)
+
+    def peer_attach(self, handle_blobs):
+        """handle_blobs: the peer_export() bytes of every rank, in rank order"""
+        arr = (PeerHandles * len(handle_blobs))()
+        for i, b in enumerate(handle_blobs):
+            C.memmove(C.byref(arr[i]), b, C.sizeof(PeerHandles))
+        self._check(self.L.shx_peer_attach(self._h, arr))
 
     def strip_erode_begin(self, cycles, seed=0):
         self._check(self.L.shx_strip_erode_begin(self._h, cycles, seed))

@@ -69,6 +69,12 @@ struct shx_ctx {
   bool tracks_clean = true; // all track accumulators are zero (world.h:56-61 already satisfied)
   LaunchShape shape[2];     // multi-CTA launch shapes: [0] spread, [1] dense
   bool forced_shape = false;
+  // peer mode
+  bool peer = false, peer_attached = false;
+  PeerView pv{};
+  unsigned long long* d_inbox = nullptr;
+  unsigned peer_seq = 0;
+  void* peer_opened[3 * kMaxPeers] = {};
   bool timing = false;
   std::vector<TimingSpan> spans;
   bool strip_open = false;  // between shx_strip_erode_begin and _end
@@ -154,6 +160,9 @@ void shx_destroy(shx_ctx* c) {
   cudaFree(c->d_drops); cudaFree(c->d_xy); cudaFree(c->d_bar); cudaFree(c->d_stats); cudaFree(c->d_flags);
   cudaFree(c->d_trace); cudaFree(c->d_u32); cudaFree(c->d_halo_ref[0]); cudaFree(c->d_halo_ref[1]);
   cudaFree(c->d_stage);
+  for (void* p : c->peer_opened)
+    if (p) cudaIpcCloseMemHandle(p);
+  cudaFree(c->d_inbox);
   if (c->h_stats) cudaFreeHost(c->h_stats);
   if (c->h_flags) cudaFreeHost(c->h_flags);
   delete c;
@@ -168,10 +177,21 @@ int shx_create(shx_ctx** out, const shx_params* p, const shx_config* cfg_in) {
   shx_config cfg;
   if (cfg_in) cfg = *cfg_in; else shx_default_config(&cfg);
   const int size = p->mapsize * p->tilesize;
+  const bool peer = cfg.peer_world > 1;
+  if (peer) {  // one strip of a world shared over NVLink: no halo, rows fixed by the rank
+    if (cfg.peer_world > kMaxPeers || cfg.peer_rank < 0 || cfg.peer_rank >= cfg.peer_world) return fail(SHX_ERR_ARG, "bad peer rank/world");
+    const int rows = size / cfg.peer_world;
+    if (rows * cfg.peer_world != size || (rows & (rows - 1)) || rows % p->tilesize)
+      return fail(SHX_ERR_ARG, "peer mode needs size/world to be a power of two and a multiple of tilesize");
+    if (cfg.mode == SHX_MODE_SEQUENTIAL) return fail(SHX_ERR_MODE, "peer mode is batched only");
+    cfg.row0 = cfg.peer_rank * rows;
+    cfg.row1 = cfg.row0 + rows;
+    cfg.halo = 0;
+  }
   if (cfg.row0 == 0 && cfg.row1 == 0) cfg.row1 = size;
   if (cfg.row0 < 0 || cfg.row1 > size || cfg.row0 >= cfg.row1) return fail(SHX_ERR_ARG, "bad strip rows");
   const bool whole = cfg.row0 == 0 && cfg.row1 == size;
-  if (!whole && cfg.halo < 2) return fail(SHX_ERR_ARG, "strip halo must be >= 2 rows");
+  if (!whole && !peer && cfg.halo < 2) return fail(SHX_ERR_ARG, "strip halo must be >= 2 rows");
   if (!whole && cfg.mode == SHX_MODE_SEQUENTIAL) return fail(SHX_ERR_MODE, "sequential mode is whole-map only");
 
   int ndev = 0;
@@ -232,12 +252,34 @@ int shx_create(shx_ctx** out, const shx_params* p, const shx_config* cfg_in) {
   cudaMemset(c->m.rec, 0, c->stored_cells * sizeof(CellRec));
   cudaMemset(c->d_stats, 0, ST_COUNT * 8);
   cudaMemset(c->d_flags, 0, 4 * sizeof(int));
+  c->peer = peer;
+  if (peer) {
+    if (cudaMalloc((void**)&c->d_inbox, 3 * kMaxPeers * sizeof(unsigned long long)) != cudaSuccess) {
+      shx_destroy(c);
+      return fail(SHX_ERR_NOMEM, "cudaMalloc failed for the peer inbox");
+    }
+    cudaMemset(c->d_inbox, 0, 3 * kMaxPeers * sizeof(unsigned long long));
+    const int rows = cfg.row1 - cfg.row0;
+    int shift = 0;
+    while ((1 << shift) < rows) shift++;
+    c->pv.shift = shift;
+    c->pv.mask = rows - 1;
+    c->pv.nranks = cfg.peer_world;
+    c->pv.rank = cfg.peer_rank;
+    c->pv.hq[cfg.peer_rank] = c->m.hq;
+    c->pv.rec[cfg.peer_rank] = c->m.rec;
+    c->pv.inbox[cfg.peer_rank] = c->d_inbox;
+  }
 
   // Launch shapes of the multi-CTA descend kernel, both with the cooperative gather.  [0] "spread":
   // CTAs of 64 so that a few thousand drops still cover all SMs (latency-bound regime); [1] "dense":
   // 2 x 448 threads per SM at 72 registers (throughput regime, >= ~256 drops per SM).  An explicit
   // block_threads / variant / coop / grid_blocks in the config forces one shape for both.
   const bool forced = cfg.block_threads > 0 || cfg.variant > 0 || cfg.coop > 0 || cfg.grid_blocks > 0;
+  if (forced && peer) {
+    shx_destroy(c);
+    return fail(SHX_ERR_ARG, "peer mode does not take launch-shape overrides");
+  }
   for (int i = 0; i < 2; i++) {
     LaunchShape& ls = c->shape[i];
     if (forced) {
@@ -248,10 +290,10 @@ int shx_create(shx_ctx** out, const shx_params* p, const shx_config* cfg_in) {
       ls.kernel = big_kernel(ls.block, cfg.variant, cfg.coop == 1);
     } else if (i == 0) {
       ls.block = 64;
-      ls.kernel = big_kernel(64, 2, true);
+      ls.kernel = peer ? (const void*)descend_lockstep_kernel<128, 7, true, true> : big_kernel(64, 2, true);
     } else {
       ls.block = 448;
-      ls.kernel = big_kernel(448, 3, true);
+      ls.kernel = peer ? (const void*)descend_lockstep_kernel<448, 2, true, true> : big_kernel(448, 3, true);
     }
     int nb = 0;
     if (cudaFuncSetAttribute(ls.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)descend_smem(ls.block)) != cudaSuccess ||
@@ -424,10 +466,15 @@ int shx_download_raw(shx_ctx* c, int32_t* hq2, void* rec32) {
 static int fetch_stats(shx_ctx* c, shx_stats* out) {
   CU(cudaMemcpyAsync(c->h_stats, c->d_stats, ST_COUNT * 8, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(c->h_flags + 2, c->d_flags + 2, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   if (out) {
     memcpy(out, c->h_stats, sizeof(shx_stats));
     out->launches = c->launches;
+  }
+  if (c->peer && c->h_flags[2]) {
+    CU(cudaMemsetAsync(c->d_flags + 2, 0, sizeof(int), c->stream));
+    return fail(SHX_ERR_PEER, "a peer GPU did not reach a phase barrier within the time-out; the call's result is invalid");
   }
   if (c->h_flags[0]) {
     CU(cudaMemsetAsync(c->d_flags, 0, sizeof(int), c->stream));
@@ -474,8 +521,39 @@ int shx_ema(shx_ctx* c) {
 // march n drops already in c->d_drops
 static int run_device_drops(shx_ctx* c, size_t n, bool trace) {
   c->last_n = n;
-  if (n == 0) return SHX_OK;
   if (n > c->max_drops) return fail(SHX_ERR_CAPACITY, "more drops than max_drops");
+  if (c->peer) {
+    // exactly ONE launch per call on every rank (even with no drops of its own): the kernels of
+    // all ranks meet at every phase barrier
+    if (!c->peer_attached) return fail(SHX_ERR_PEER, "shx_peer_attach has not been called");
+    const LaunchShape& ls = c->shape[(n > (size_t)c->sm_count * 256) ? 1 : 0];
+    if (n > (size_t)ls.cap_blocks * ls.block) return fail(SHX_ERR_CAPACITY, "peer mode runs a call's drops in one launch");
+    c->tracks_clean = false;
+    DescendArgs a;
+    a.m = c->m;
+    a.pv = c->pv;
+    a.pv.tag_base = ((++c->peer_seq) & 0xFFFu) << 20;
+    a.P = step_params(c->p);
+    a.drops = c->d_drops;
+    a.ndrops = (unsigned)n;
+    a.bar = c->d_bar;
+    a.stats = c->d_stats;
+    a.trace = trace ? c->d_trace : nullptr;
+    a.trace_cap = c->trace_cap;
+    a.trace_n = trace ? c->d_flags + 1 : nullptr;
+    CU(cudaMemsetAsync(c->d_bar, 0, sizeof(GridBar), c->stream));
+    // every strip's reset / spawn is complete before anybody's first phase touches it
+    peer_handshake_kernel<<<1, 1, 0, c->stream>>>(a.pv, a.pv.tag_base, &c->d_bar->abort);
+    c->launches++;
+    void* args[] = {&a};
+    const int grid = (int)std::max<size_t>(1, (n + ls.block - 1) / ls.block);
+    CU(cudaLaunchCooperativeKernel(ls.kernel, dim3(grid), dim3(ls.block), args, descend_smem(ls.block), c->stream));
+    c->launches++;
+    // a peer that never arrived aborts the launch; surface it with the next stats read
+    CU(cudaMemcpyAsync(c->d_flags + 2, &c->d_bar->abort, sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
+    return SHX_OK;
+  }
+  if (n == 0) return SHX_OK;
   c->tracks_clean = false;
   if (sequential(c)) {
     SequentialArgs a;
@@ -865,6 +943,65 @@ int shx_strip_erode_end(shx_ctx* c) {
   if (rc) return rc;
   if ((rc = ema_launch(c, !c->cfg.keep_tracks))) return rc;  // world.h:81-86
   return span_end(c);
+}
+
+// ------------------------------------------------------------------------------- peer mode
+
+int shx_peer_export(shx_ctx* c, shx_peer_handles* out) {
+  if (!c || !out) return fail(SHX_ERR_ARG, "null argument");
+  if (!c->peer) return fail(SHX_ERR_MODE, "context was not created with peer_world > 1");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CU(cudaSetDevice(c->cfg.device));
+  // An IPC handle names the whole allocation a pointer lives in and opens at that allocation's
+  // base; small cudaMalloc blocks are sub-allocated, so the offset has to travel with the handle.
+  typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  CU(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr));
+  if (!fn) return fail(SHX_ERR_CUDA, "cuMemGetAddressRange is not available");
+  const void* ptr[3] = {c->m.hq, c->m.rec, c->d_inbox};
+  unsigned char* dst[3] = {out->hq, out->rec, out->inbox};
+  uint64_t* off[3] = {&out->off_hq, &out->off_rec, &out->off_inbox};
+  for (int k = 0; k < 3; k++) {
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (reinterpret_cast<range_fn>(fn)(&base, &size, (unsigned long long)ptr[k]) != 0)
+      return fail(SHX_ERR_CUDA, "cuMemGetAddressRange failed");
+    *off[k] = (unsigned long long)ptr[k] - base;
+    CU(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(dst[k]), const_cast<void*>(ptr[k])));
+  }
+  return SHX_OK;
+}
+
+int shx_peer_attach(shx_ctx* c, const shx_peer_handles* all) {
+  if (!c || !all) return fail(SHX_ERR_ARG, "null argument");
+  if (!c->peer) return fail(SHX_ERR_MODE, "context was not created with peer_world > 1");
+  if (c->peer_attached) return fail(SHX_ERR_ARG, "already attached");
+  CU(cudaSetDevice(c->cfg.device));
+  for (int r = 0; r < c->pv.nranks; r++) {
+    if (r == c->pv.rank) continue;
+    char* p[3] = {nullptr, nullptr, nullptr};
+    const unsigned char* h[3] = {all[r].hq, all[r].rec, all[r].inbox};
+    const uint64_t off[3] = {all[r].off_hq, all[r].off_rec, all[r].off_inbox};
+    for (int k = 0; k < 3; k++) {
+      cudaIpcMemHandle_t handle;
+      memcpy(&handle, h[k], sizeof handle);
+      // the same allocation may back several buffers: it can only be opened once per process
+      for (int j = 0; j < k && !p[k]; j++)
+        if (memcmp(h[j], h[k], sizeof handle) == 0) p[k] = p[j];
+      if (!p[k]) {
+        void* base = nullptr;
+        CU(cudaIpcOpenMemHandle(&base, handle, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_opened[3 * r + k] = base;
+        p[k] = static_cast<char*>(base);
+      }
+    }
+    c->pv.hq[r] = reinterpret_cast<int2*>(p[0] + off[0]);
+    c->pv.rec[r] = reinterpret_cast<CellRec*>(p[1] + off[1]);
+    c->pv.inbox[r] = reinterpret_cast<unsigned long long*>(p[2] + off[2]);
+  }
+  c->peer_attached = true;
+  return SHX_OK;
 }
 
 #ifdef SHX_PHASE_TIMING

@@ -38,11 +38,28 @@ struct GridBar {
   // active"; both monotonically increasing over the launch (zeroed by the host before it)
   unsigned long long word[2];
   unsigned max_steps;  // longest drop of this launch == number of phases that had a live drop
-  unsigned pad[3];
+  unsigned abort;      // peer mode: a peer did not show up in time
+  // peer mode: {phase+1 | box-wide active sum << 32}, written by block 0 once every GPU has arrived
+  unsigned long long release[2];
+};
+
+// Peer mode (one world spread over the GPUs of a box, one process per GPU): every rank maps the
+// strips of all ranks (CUDA IPC over NVLink).  A drop stays with the rank that spawned it and
+// reads / adds into whichever strip it is over; the per-phase barrier spans all GPUs, so the
+// schedule -- and therefore the result -- is exactly the single-GPU one.
+constexpr int kMaxPeers = 8;
+struct PeerView {
+  int2* hq[kMaxPeers];                  // strip r holds rows [r*rows, (r+1)*rows)
+  CellRec* rec[kMaxPeers];
+  unsigned long long* inbox[kMaxPeers]; // rank r's inbox: [parity][sender] words {phase+1 | sum << 32}
+  int shift, mask;                      // rows per strip = 1 << shift
+  int nranks, rank;
+  unsigned tag_base;                    // (launch sequence number) << 20, identical on every rank
 };
 
 struct DescendArgs {
   MapView m;
+  PeerView pv;
   StepParams P;
   shx_drop* drops;
   unsigned ndrops;
@@ -104,6 +121,102 @@ __device__ __forceinline__ unsigned grid_barrier_sum(GridBar* bar, unsigned phas
   return *s_total;
 }
 
+// The same barrier across the GPUs of the box (peer mode).  Local CTAs arrive on the local word as
+// above; block 0 waits for them, publishes {phase+1 | local sum} into every rank's inbox over NVLink,
+// waits until all ranks have published, and releases the local CTAs with the box-wide sum.  All
+// fences are system scope: the REDs a CTA sent into a peer's strip must be performed before its
+// arrival can be observed anywhere.  A peer that does not show up within ~2 s aborts the launch
+// (sum 0) instead of hanging the GPU.
+__device__ __forceinline__ unsigned peer_barrier_sum(GridBar* bar, const PeerView& pv, unsigned phase, unsigned block_sum,
+                                                     unsigned* s_total, unsigned* s_remote, unsigned& prev_hi0,
+                                                     unsigned& prev_hi1) {
+  if (threadIdx.x == 0) {
+    const unsigned par = phase & 1u;
+    unsigned long long* w = &bar->word[par];
+    // release: system scope only if this CTA sent REDs over NVLink during the phase (the caller's
+    // __syncthreads_count ordered every thread's s_remote store before this read)
+    if (*s_remote) {
+      asm volatile("fence.acq_rel.sys;" ::: "memory");
+      *s_remote = 0u;
+    } else {
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    }
+    atomicAdd(w, ((unsigned long long)block_sum << 32) | 1ull);
+    const unsigned tag = pv.tag_base + phase + 1u;  // unique per launch and phase: inbox words are never reset
+    const long long t0 = clock64();
+    bool dead = false;
+    if (blockIdx.x == 0) {
+      const unsigned target = (phase / 2u + 1u) * gridDim.x;
+      unsigned long long seen;
+      do {
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(w) : "memory");
+      } while ((int)((unsigned)seen - target) < 0);
+      const unsigned hi = (unsigned)(seen >> 32);
+      const unsigned local = hi - (par ? prev_hi1 : prev_hi0);
+      if (par) prev_hi1 = hi;
+      else prev_hi0 = hi;
+      asm volatile("fence.acq_rel.sys;" ::: "memory");
+      const unsigned long long msg = ((unsigned long long)local << 32) | tag;
+      for (int r = 0; r < pv.nranks; r++) {
+        unsigned long long* slot = pv.inbox[r] + par * kMaxPeers + pv.rank;
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(slot), "l"(msg) : "memory");
+      }
+      unsigned total = 0;
+      for (int r = 0; r < pv.nranks && !dead; r++) {
+        const unsigned long long* slot = pv.inbox[pv.rank] + par * kMaxPeers + r;
+        unsigned long long got;
+        do {
+          asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(slot) : "memory");
+          if ((unsigned)got != tag && clock64() - t0 > 4000000000ll) dead = true;
+        } while ((unsigned)got != tag && !dead);
+        total += (unsigned)(got >> 32);
+      }
+      asm volatile("fence.acq_rel.sys;" ::: "memory");
+      if (dead) { total = 0; bar->abort = 1u; }
+      const unsigned long long rel = ((unsigned long long)total << 32) | tag;
+      asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(&bar->release[par]), "l"(rel) : "memory");
+      *s_total = total;
+    } else {
+      unsigned long long got;
+      do {
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(got) : "l"(&bar->release[par]) : "memory");
+        if ((unsigned)got != tag && clock64() - t0 > 8000000000ll) { dead = true; got = tag; }
+      } while ((unsigned)got != tag);
+      // device scope is enough here: block 0 acquired the peers' writes at system scope before it
+      // stored the release word, and causality order is transitive
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      *s_total = dead ? 0u : (unsigned)(got >> 32);
+    }
+  }
+  __syncthreads();
+  return *s_total;
+}
+
+// Start-of-call handshake of peer mode, stream-ordered between this rank's track reset / spawn and
+// its descend launch: no rank may add into a strip whose owner has not finished resetting it.
+// Uses the third inbox row; <<<1, 1>>>.
+__global__ void peer_handshake_kernel(const PeerView pv, unsigned tag, unsigned* abort_flag) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  asm volatile("fence.acq_rel.sys;" ::: "memory");
+  for (int r = 0; r < pv.nranks; r++) {
+    unsigned long long* slot = pv.inbox[r] + 2 * kMaxPeers + pv.rank;
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(slot), "l"((unsigned long long)tag) : "memory");
+  }
+  const long long t0 = clock64();
+  for (int r = 0; r < pv.nranks; r++) {
+    const unsigned long long* slot = pv.inbox[pv.rank] + 2 * kMaxPeers + r;
+    unsigned long long got;
+    do {
+      asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(slot) : "memory");
+      if ((unsigned)got != tag && clock64() - t0 > 20000000000ll) {  // ~10 s: ranks may reach the call at different times
+        *abort_flag = 1u;
+        return;
+      }
+    } while ((unsigned)got != tag);
+  }
+  asm volatile("fence.acq_rel.sys;" ::: "memory");
+}
+
 // order-preserving float <-> uint32 maps (for non-NaN inputs; -0 must be canonicalised by the caller)
 __device__ __forceinline__ unsigned f2ord(float f) {
   const unsigned b = __float_as_uint(f);
@@ -139,22 +252,49 @@ __device__ __forceinline__ float ord2f(unsigned u) {
 // Shared memory per thread: s_B[9] block heights (thread-major, stride 9: conflict-free both for
 // the owner's sequential reads and for the cooperative stores), s_D[2][8] neighbour deltas of this
 // / the previous phase, s_S[8] (height, index) pairs in cascade order.
-template <int kMaxThreads, int kMinBlocks, bool kCoop>
+template <int kMaxThreads, int kMinBlocks, bool kCoop, bool kPeer = false>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kernel(const __grid_constant__ DescendArgs a) {
+  static_assert(kCoop || !kPeer, "peer mode uses the cooperative gather");
   extern __shared__ int32_t s_mem[];
   __shared__ unsigned s_total;
+  __shared__ unsigned s_remote;  // peer mode: this CTA added into another GPU's strip during the phase
   const int tid = threadIdx.x, nt = blockDim.x;
+  if (kPeer) {
+    if (tid == 0) s_remote = 0u;
+    __syncthreads();
+  }
   int32_t* s_B = s_mem + tid * 9;                               // s_B[k]
   int32_t* s_D = s_mem + 9 * nt + tid;                          // s_D[(buf*8 + j)*nt]
   uint2* s_S = reinterpret_cast<uint2*>(s_mem + 25 * nt) + tid; // s_S[r*nt]
   // cooperative gather: lane -> (which of 3 drops of a group, which of its 9 cells)
   const int lane = tid & 31;
   const int co_k = lane % 9, co_sub = lane / 9;
-  const int co_off = (co_k / 3 - 1) * a.m.size + (co_k % 3 - 1);
+  const int co_dx = co_k / 3 - 1, co_dy = co_k % 3 - 1;
+  const int co_off = co_dx * a.m.size + co_dy;
   int32_t* const s_Bw = s_mem + (tid - lane) * 9;               // first drop of this warp
   const unsigned gid = blockIdx.x * nt + tid;
   const int size = a.m.size;
   int* const H = reinterpret_cast<int*>(a.m.hq);
+  // cell (x, y) -> its pair of height words / its record.  Peer mode: the strip x >> shift owns it.
+  auto h_at = [&](int x, int y) -> int* {
+    if (kPeer) return reinterpret_cast<int*>(a.pv.hq[x >> a.pv.shift]) + 2 * ((x & a.pv.mask) * size + y);
+    return H + 2 * ((x - a.m.xlo) * size + y);
+  };
+  auto rec_at = [&](int x, int y) -> CellRec* {
+    if (kPeer) return a.pv.rec[x >> a.pv.shift] + ((x & a.pv.mask) * size + y);
+    return a.m.rec + ((x - a.m.xlo) * size + y);
+  };
+  // Integer adds.  Peer mode: every add into a strip is performed by the L2 of the GPU that holds it;
+  // the owner uses plain device-scope REDs, the others system-scope ones over NVLink, and a CTA
+  // that sent anything off-device raises s_remote so that its arrival fence is system scope.
+  auto add32 = [&](int* p, int v, int x) {
+    if (kPeer && (x >> a.pv.shift) != a.pv.rank) { atomicAdd_system(p, v); s_remote = 1u; }
+    else atomicAdd(p, v);
+  };
+  auto add64 = [&](unsigned long long* p, unsigned long long v, int x) {
+    if (kPeer && (x >> a.pv.shift) != a.pv.rank) { atomicAdd_system(p, v); s_remote = 1u; }
+    else atomicAdd(p, v);
+  };
 
   DropRegs d;
   d.px = d.py = d.sx = d.sy = d.vol = d.sed = 0.0f;
@@ -170,7 +310,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
   // deltas of the previous phase, still owed to the other plane
   int dC_prev = 0;          // centre
   unsigned dmask_prev = 0;  // neighbours (values in s_D)
-  int pidx = 0;
+  int pix = 0, piy = 0;     // its centre cell
   unsigned bar_hi0 = 0, bar_hi1 = 0;  // grid barrier bookkeeping (thread 0)
   unsigned steps = 0, transfers = 0;
   long long fx_eroded = 0, fx_inflation = 0;
@@ -218,12 +358,18 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
 #pragma unroll
         for (int g = 0; g < 11; g++) {
           const int src = g * 3 + co_sub;
-          const int c = __shfl_sync(0xffffffffu, cidx, src & 31);
           const unsigned m = __shfl_sync(0xffffffffu, meta, src & 31);
           const bool ok = co_sub < 3 && src < 32 && ((m >> co_k) & 1u) && (m & 0x200u);
-          got[g] = ok ? __ldcg(H + 2 * (c + co_off) + rpar) : 0;
+          if (kPeer) {
+            const int sx = __shfl_sync(0xffffffffu, ix, src & 31), sy = __shfl_sync(0xffffffffu, iy, src & 31);
+            got[g] = 0;
+            if (ok) got[g] = __ldcg(h_at(sx + co_dx, sy + co_dy) + rpar);  // coordinates are only valid when ok
+          } else {
+            const int c = __shfl_sync(0xffffffffu, cidx, src & 31);
+            got[g] = ok ? __ldcg(H + 2 * (c + co_off) + rpar) : 0;
+          }
         }
-        if (alive) fld = __ldg(reinterpret_cast<const float4*>(a.m.rec + cidx));
+        if (alive) fld = __ldg(reinterpret_cast<const float4*>(rec_at(ix, iy)));
 #pragma unroll
         for (int g = 0; g < 11; g++) {
           const int src = g * 3 + co_sub;
@@ -241,14 +387,14 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
     }
 
     if (dC_prev | (int)dmask_prev) {  // catch-up of the previous phase's deltas
-      if (dC_prev && !SHX_EXP(2)) atomicAdd(H + 2 * pidx + wpar, dC_prev);
+      if (dC_prev && !SHX_EXP(2)) add32(h_at(pix, piy) + wpar, dC_prev, pix);
       unsigned m = dmask_prev;
       while (m) {
         const int j = __ffs(m) - 1;
         m &= m - 1u;
         const int k = j + (j >> 2);
-        const int off = ((k * 11) >> 5) * size - size + (k - 3 * ((k * 11) >> 5)) - 1;
-        if (!SHX_EXP(2)) atomicAdd(H + 2 * (pidx + off) + wpar, s_D[(prev + j) * nt]);
+        const int kx = (k * 11) >> 5;
+        if (!SHX_EXP(2)) add32(h_at(pix + kx - 1, piy + (k - 3 * kx) - 1) + wpar, s_D[(prev + j) * nt], pix + kx - 1);
       }
       dC_prev = 0;
       dmask_prev = 0;
@@ -318,11 +464,10 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
                 Bc -= s;
                 const int k = (int)(j + (j >> 2));
                 const int kx = (k * 11) >> 5;
-                const int off = kx * size - size + (k - 3 * kx) - 1;
                 s_B[k] += s;
                 s_D[(cur + (int)j) * nt] = s;
                 dmask |= 1u << j;
-                if (!SHX_EXP(2)) atomicAdd(H + 2 * (cidx + off) + wpar, s);
+                if (!SHX_EXP(2)) add32(h_at(ix + kx - 1, iy + (k - 3 * kx) - 1) + wpar, s, ix + kx - 1);
                 transfers++;
               }
             }
@@ -355,16 +500,16 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
         if (!mv.oob) {
           const int ddx = nix - ix, ddy = niy - iy;
           if (ddx >= -1 && ddx <= 1 && ddy >= -1 && ddy <= 1) hv = s_B[(ddx + 1) * 3 + (ddy + 1)];
-          else hv = __ldcg(H + 2 * ((nix - a.m.xlo) * size + niy) + rpar);
+          else hv = __ldcg(h_at(nix, niy) + rpar);
         }
         const float cap = 1.0f + a.P.entrainment * shx_erff(0.4f * fld.x);  // water.h:127, cellpool.h:242-244
         if (!SHX_EXP(1)) {  // water.h:115-117.  discharge (>= 0, low word) and momentum-x (high word)
           // go out as ONE 64-bit add: the low word cannot carry while the Q13.18 range check holds
-          CellRec* rec = a.m.rec + cidx;
+          CellRec* rec = rec_at(ix, iy);
           const unsigned long long packed = ((unsigned long long)(unsigned)t_quantize(mv.t_mx) << 32) |
                                             (unsigned long long)(unsigned)t_quantize(mv.t_d);
-          atomicAdd(reinterpret_cast<unsigned long long*>(&rec->track_d), packed);
-          atomicAdd(&rec->track_my, t_quantize(mv.t_my));
+          add64(reinterpret_cast<unsigned long long*>(&rec->track_d), packed, ix);
+          add32(&rec->track_my, t_quantize(mv.t_my), ix);
         }
         const float h2 = mv.oob ? oob_h2(hc) : h_to_float(hv);  // water.h:121-124
         float carried;
@@ -383,7 +528,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
         } else {
           d.age++;                      // water.h:153
           d.flags |= SHX_DROP_CASCADE;  // water.h:151, executed at the start of the next phase
-          if (nix < a.m.row0 || nix >= a.m.row1) {  // left the strip: hand over (cascade still owed)
+          if (!kPeer && (nix < a.m.row0 || nix >= a.m.row1)) {  // left the strip: hand over (cascade still owed)
             const bool tolo = nix < a.m.row0;
             d.flags = (d.flags & ~SHX_DROP_ALIVE) | (tolo ? SHX_DROP_MIGRATE_LO : SHX_DROP_MIGRATE_HI);
             alive = false;
@@ -393,10 +538,11 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
         }
         SHX_TRACE_ROW();
       }
-      if (dC && !SHX_EXP(2)) atomicAdd(H + 2 * cidx + wpar, dC);
+      if (dC && !SHX_EXP(2)) add32(h_at(ix, iy) + wpar, dC, ix);
       dC_prev = dC;
       dmask_prev = dmask;
-      pidx = cidx;
+      pix = ix;
+      piy = iy;
     }
 
     SHX_T(4);
@@ -412,7 +558,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
 #endif
     const unsigned block_sum = (unsigned)__syncthreads_count(alive || (dC_prev | (int)dmask_prev));
     SHX_T(5);
-    const unsigned total = grid_barrier_sum(a.bar, phase, block_sum, &s_total, bar_hi0, bar_hi1);
+    const unsigned total = kPeer ? peer_barrier_sum(a.bar, a.pv, phase, block_sum, &s_total, &s_remote, bar_hi0, bar_hi1)
+                                 : grid_barrier_sum(a.bar, phase, block_sum, &s_total, bar_hi0, bar_hi1);
     SHX_T(6);
 #ifdef SHX_PHASE_TIMING
     if (gid == 0 && alive) {

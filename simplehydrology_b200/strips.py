@@ -213,6 +213,44 @@ class GpuStrip:
         return self.W.read_stats()
 
 
+class PeerWorld:
+    """One world spread over the GPUs of a box, one process per GPU (`shx_config.peer_world`).
+
+    Unlike the exchange-round strips above, nothing is exchanged by the host: every rank maps the
+    other ranks' strips through CUDA IPC once, and the descend kernel itself reads and adds into the
+    strip a drop happens to be over (NVLink peer loads / system-scope REDs) and synchronises all
+    GPUs at every phase.  The schedule is the single-GPU lock step, so the result is bit-identical
+    to a one-GPU run of the same world.  torch.distributed is only used to pass the IPC handles
+    around at start-up."""
+
+    def __init__(self, mapsize, rank, world, device, params=None, max_drops=0):
+        import simplehydrology_b200 as shx
+        p = params if params is not None else shx.default_params(mapsize)
+        size = p.mapsize * p.tilesize
+        rows = size // world
+        self.rank, self.world, self.size = rank, world, size
+        self.row0, self.row1 = rank * rows, (rank + 1) * rows
+        nodes = (rows // p.tilesize) * p.mapsize
+        self.W = shx.World(params=p, device=device, peer_rank=rank, peer_world=world,
+                           max_drops=max_drops or max(4096, nodes * 1024))
+        blob = self.W.peer_export()
+        blobs = [None] * world
+        dist.all_gather_object(blobs, blob)
+        self.W.peer_attach(blobs)
+        dist.barrier()
+
+    def erode_async(self, cycles, seed=0):
+        self.W.erode_async(cycles, seed)
+
+    def erode(self, cycles, seed=0):
+        return self.W.erode(cycles, seed)
+
+    def close(self):
+        if dist.is_initialized():
+            dist.barrier()  # nobody unmaps while a peer may still be inside a kernel
+        self.W.close()
+
+
 def all_reduce_stats(st, device):
     """sum the counters of a Stats struct over ranks (phases: max)"""
     names = [n for n, _ in type(st)._fields_]
