@@ -187,7 +187,7 @@ def run_cuda(args):
         if world == 1 or peer:
             W.erode_async(CYCLES, SEED)
         else:
-            ex.erode(CYCLES, SEED)
+            (ex.erode_cycle if args.multi == "cycle" else ex.erode)(CYCLES, SEED)
         return W.read_stats()  # one stream sync + 128-byte read per cycle
 
     for _ in range(args.warmup):
@@ -246,7 +246,9 @@ def run_cuda(args):
                 "config": {"workload": "8192x8192 world (mapsize 16, BASELINE configs[3]); one step = one erode(512) cycle: 131072 drops, "
                                        "lock-step batched descend + cascade, EMA",
                            "map": "8192x8192", "drops_per_cycle": MAPSIZE * MAPSIZE * CYCLES,
-                           "parallelism": (f"row strips x{world}, peer-mapped over NVLink, one cross-GPU barrier per phase" if peer else f"row strips x{world}, exchange rounds") if world > 1 else "single GPU",
+                           "parallelism": {"peer": f"row strips x{world}, peer-mapped over NVLink, one cross-GPU barrier per phase (bit-identical to 1 GPU)",
+                                            "cycle": f"row strips x{world}, halo rows and border-crossing drops exchanged once per cycle (NCCL send/recv)",
+                                            "rounds": f"row strips x{world}, exchange rounds until no drop is in flight"}[args.multi] if world > 1 else "single GPU",
                            "l2": "inputs larger than L2 (2.7 GB of map state vs 126 MB): no flush needed", "seed": SEED},
                 "cycles_per_s": args.steps / (ms * 1e-3),
                 "mean_steps_per_drop": psteps / max(total["spawned"], 1),
@@ -336,7 +338,8 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--e2e-mask", default="all", choices=["all", "hdm"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--multi", default="peer", choices=["peer", "strips"], help="N > 1: peer-mapped lock step (default) or exchange-round strips")
+    ap.add_argument("--multi", default="cycle", choices=["cycle", "peer", "rounds"],
+                    help="N > 1: strips exchanging once per cycle (default), peer-mapped lock step, or exchange rounds")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

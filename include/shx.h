@@ -227,6 +227,9 @@ int shx_strip_run_device_drops(shx_ctx* c, const shx_drop* dev_drops, size_t n, 
  *   end   = EMA of the owned rows (world.h:81-86)
  * stats accumulate from begin to end (shx_read_stats after end). */
 int shx_strip_erode_begin(shx_ctx* c, int cycles, uint64_t seed);
+/* the same with `n_carried` drops (device buffer) appended to the spawned batch: the drops the
+ * neighbours handed over at the end of the previous call, when strips exchange once per call */
+int shx_strip_erode_begin_with(shx_ctx* c, int cycles, uint64_t seed, const shx_drop* dev_carried, size_t n_carried);
 int shx_strip_erode_end(shx_ctx* c);
 
 /* ---- peer mode (shx_config.peer_world > 1): export this rank's strip, map everybody's */

@@ -626,6 +626,10 @@ void orc_ls_run(orc_ls_world* w, orc_drop* drops, size_t n, orc_stats* st, float
     for (size_t i = 0; i < n; i++) {
       has[i] = 0;
       if (!(drops[i].flags & ORC_DROP_ALIVE)) continue;
+      if (w->align_age && (uint64_t)drops[i].age > phase) { /* still asleep: counts as active, does nothing */
+        active++;
+        continue;
+      }
       has[i] = (unsigned char)ls_step(w, R, &drops[i], deltas + 9 * i, &dpos[2 * i], &dpos[2 * i + 1], &local);
       if (drops[i].flags & (ORC_DROP_DONE_AGE | ORC_DROP_DONE_VOL | ORC_DROP_DONE_OOB)) drops[i].flags &= ~ORC_DROP_ALIVE;
       active++;

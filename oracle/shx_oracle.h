@@ -122,6 +122,7 @@ typedef struct {
   float* field;     /* 4 floats per cell: discharge, momentumx, momentumy, rootdensity */
   orc_track* track; /* Q13.18 accumulators */
   int row0, row1;   /* rows [row0,row1) are owned (strip); 0,size for the whole map */
+  int align_age;    /* != 0: a drop of age a sleeps until phase a (drops carried over from the previous call) */
 } orc_ls_world;
 
 orc_ls_world* orc_ls_create(const orc_params* p);

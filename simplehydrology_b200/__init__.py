@@ -122,6 +122,7 @@ def lib():
     L.shx_strip_pack_migrants.argtypes = [vp, vp, vp, sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.shx_strip_run_device_drops.argtypes = [vp, vp, sz, C.POINTER(Stats)]
     L.shx_strip_erode_begin.argtypes = [vp, C.c_int, u64]
+    L.shx_strip_erode_begin_with.argtypes = [vp, C.c_int, u64, vp, sz]
     L.shx_strip_erode_end.argtypes = [vp]
     L.shx_peer_export.argtypes = [vp, C.POINTER(PeerHandles)]
     L.shx_peer_attach.argtypes = [vp, C.POINTER(PeerHandles)]
@@ -325,8 +326,8 @@ class World:
             C.memmove(C.byref(arr[i]), b, C.sizeof(PeerHandles))
         self._check(self.L.shx_peer_attach(self._h, arr))
 
-    def strip_erode_begin(self, cycles, seed=0):
-        self._check(self.L.shx_strip_erode_begin(self._h, cycles, seed))
+    def strip_erode_begin(self, cycles, seed=0, carried_ptr=None, n_carried=0):
+        self._check(self.L.shx_strip_erode_begin_with(self._h, cycles, seed, carried_ptr, n_carried))
 
     def strip_erode_end(self):
         self._check(self.L.shx_strip_erode_end(self._h))

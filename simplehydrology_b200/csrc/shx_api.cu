@@ -519,7 +519,7 @@ int shx_ema(shx_ctx* c) {
 }
 
 // march n drops already in c->d_drops
-static int run_device_drops(shx_ctx* c, size_t n, bool trace) {
+static int run_device_drops(shx_ctx* c, size_t n, bool trace, bool align_age = false) {
   c->last_n = n;
   if (n > c->max_drops) return fail(SHX_ERR_CAPACITY, "more drops than max_drops");
   if (c->peer) {
@@ -536,6 +536,7 @@ static int run_device_drops(shx_ctx* c, size_t n, bool trace) {
     a.P = step_params(c->p);
     a.drops = c->d_drops;
     a.ndrops = (unsigned)n;
+    a.align_age = 0u;
     a.bar = c->d_bar;
     a.stats = c->d_stats;
     a.trace = trace ? c->d_trace : nullptr;
@@ -578,6 +579,7 @@ static int run_device_drops(shx_ctx* c, size_t n, bool trace) {
     a.m = c->m;
     a.P = step_params(c->p);
     a.drops = c->d_drops + done;
+    a.align_age = align_age ? 1u : 0u;
     a.bar = c->d_bar;
     a.stats = c->d_stats;
     a.trace = (trace && done == 0) ? c->d_trace : nullptr;
@@ -919,8 +921,9 @@ int shx_strip_run_device_drops(shx_ctx* c, const shx_drop* dev_drops, size_t n, 
   return SHX_OK;
 }
 
-int shx_strip_erode_begin(shx_ctx* c, int cycles, uint64_t seed) {
+int shx_strip_erode_begin_with(shx_ctx* c, int cycles, uint64_t seed, const shx_drop* dev_carried, size_t n_carried) {
   if (!c) return fail(SHX_ERR_ARG, "null context");
+  if (n_carried && !dev_carried) return fail(SHX_ERR_ARG, "null carried drops");
   int rc = begin_call(c);
   if (rc) return rc;
   c->strip_open = true;
@@ -928,12 +931,17 @@ int shx_strip_erode_begin(shx_ctx* c, int cycles, uint64_t seed) {
   size_t n = 0;
   if ((rc = span_begin(c, 0))) return rc;
   if ((rc = spawn_device(c, cycles, seed, c->epoch, &n))) return rc;  // world.h:64-74
+  if (n + n_carried > c->max_drops) return fail(SHX_ERR_CAPACITY, "spawned + carried drops exceed max_drops");
+  if (n_carried)  // drops handed over by the neighbours at the end of the previous call march with this call's batch
+    CU(cudaMemcpyAsync(c->d_drops + n, dev_carried, n_carried * sizeof(shx_drop), cudaMemcpyDeviceToDevice, c->stream));
   if ((rc = span_end(c))) return rc;
   c->epoch++;
   if ((rc = span_begin(c, 1))) return rc;
-  if ((rc = run_device_drops(c, n, false))) return rc;  // world.h:76
+  if ((rc = run_device_drops(c, n + n_carried, false, n_carried > 0))) return rc;  // world.h:76
   return span_end(c);
 }
+
+int shx_strip_erode_begin(shx_ctx* c, int cycles, uint64_t seed) { return shx_strip_erode_begin_with(c, cycles, seed, nullptr, 0); }
 
 int shx_strip_erode_end(shx_ctx* c) {
   if (!c) return fail(SHX_ERR_ARG, "null context");

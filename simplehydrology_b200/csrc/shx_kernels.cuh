@@ -39,7 +39,7 @@ struct GridBar {
   unsigned long long word[2];
   unsigned max_steps;  // longest drop of this launch == number of phases that had a live drop
   unsigned abort;      // peer mode: a peer did not show up in time
-  // peer mode: {phase+1 | box-wide active sum << 32}, written by block 0 once every GPU has arrived
+  // peer mode: {phase tag | box-wide active sum << 32}, stored by the publishing CTA once every GPU has arrived
   unsigned long long release[2];
 };
 
@@ -63,6 +63,7 @@ struct DescendArgs {
   StepParams P;
   shx_drop* drops;
   unsigned ndrops;
+  unsigned align_age;  // != 0: drops with age > 0 wait for the phase equal to their age
   GridBar* bar;
   unsigned long long* stats;
   float* trace;  // 7 floats per Drop::descend call of drop 0, or null
@@ -122,11 +123,15 @@ __device__ __forceinline__ unsigned grid_barrier_sum(GridBar* bar, unsigned phas
 }
 
 // The same barrier across the GPUs of the box (peer mode).  Local CTAs arrive on the local word as
-// above; block 0 waits for them, publishes {phase+1 | local sum} into every rank's inbox over NVLink,
-// waits until all ranks have published, and releases the local CTAs with the box-wide sum.  All
-// fences are system scope: the REDs a CTA sent into a peer's strip must be performed before its
-// arrival can be observed anywhere.  A peer that does not show up within ~2 s aborts the launch
-// (sum 0) instead of hanging the GPU.
+// above; block 0 waits for them, publishes {phase tag | local sum << 32} into every rank's inbox over
+// NVLink, waits until all ranks' words in its own inbox carry this phase's tag, and releases the
+// local CTAs with the box-wide sum through the release word.  Scopes: a CTA that sent REDs into a
+// peer's strip during the phase arrives behind a system-scope fence (the others behind a
+// device-scope one); block 0 fences at system scope before the inbox stores and after the inbox
+// poll; the released CTAs acquire at device scope (causality order is transitive).  System-scope
+// fences are expensive (measured: +5 ms per 8192^2 cycle when every CTA issues one per phase), which
+// is why only block 0 and the CTAs with off-device REDs pay them.  A peer that does not show up
+// within ~2 s aborts the launch (sum 0) instead of hanging the GPU.
 __device__ __forceinline__ unsigned peer_barrier_sum(GridBar* bar, const PeerView& pv, unsigned phase, unsigned block_sum,
                                                      unsigned* s_total, unsigned* s_remote, unsigned& prev_hi0,
                                                      unsigned& prev_hi1) {
@@ -161,16 +166,26 @@ __device__ __forceinline__ unsigned peer_barrier_sum(GridBar* bar, const PeerVie
         unsigned long long* slot = pv.inbox[r] + par * kMaxPeers + pv.rank;
         asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(slot), "l"(msg) : "memory");
       }
-      unsigned total = 0;
-      for (int r = 0; r < pv.nranks && !dead; r++) {
-        const unsigned long long* slot = pv.inbox[pv.rank] + par * kMaxPeers + r;
-        unsigned long long got;
-        do {
-          asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(slot) : "memory");
-          if ((unsigned)got != tag && clock64() - t0 > 4000000000ll) dead = true;
-        } while ((unsigned)got != tag && !dead);
-        total += (unsigned)(got >> 32);
-      }
+      // poll all ranks' words of this GPU's inbox row together: one L2 round trip per sweep
+      const unsigned long long* row = pv.inbox[pv.rank] + par * kMaxPeers;
+      unsigned total;
+      bool all;
+      do {
+        unsigned long long got[kMaxPeers];
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; r++) {
+          got[r] = tag;
+          if (r < pv.nranks) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got[r]) : "l"(row + r) : "memory");
+        }
+        all = true;
+        total = 0;
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; r++) {
+          all = all && (unsigned)got[r] == tag;
+          total += r < pv.nranks ? (unsigned)(got[r] >> 32) : 0u;
+        }
+        if (!all && clock64() - t0 > 4000000000ll) dead = true;
+      } while (!all && !dead);
       asm volatile("fence.acq_rel.sys;" ::: "memory");
       if (dead) { total = 0; bar->abort = 1u; }
       const unsigned long long rel = ((unsigned long long)total << 32) | tag;
@@ -182,8 +197,6 @@ __device__ __forceinline__ unsigned peer_barrier_sum(GridBar* bar, const PeerVie
         asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(got) : "l"(&bar->release[par]) : "memory");
         if ((unsigned)got != tag && clock64() - t0 > 8000000000ll) { dead = true; got = tag; }
       } while ((unsigned)got != tag);
-      // device scope is enough here: block 0 acquired the peers' writes at system scope before it
-      // stored the release word, and causality order is transitive
       asm volatile("fence.acq_rel.gpu;" ::: "memory");
       *s_total = dead ? 0u : (unsigned)(got >> 32);
     }
@@ -307,6 +320,10 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
     d.vol = hi.x; d.sed = hi.y; d.age = __float_as_int(hi.z); d.flags = __float_as_int(hi.w);
   }
   bool alive = (d.flags & SHX_DROP_ALIVE) != 0;
+  // align_age: a drop carried over from the previous call sleeps until the phase that equals its age,
+  // i.e. it meets the drops of this call at the same age at which it met those of its own call
+  bool asleep = a.align_age != 0u && alive && d.age > 0;
+  alive = alive && !asleep;
   // deltas of the previous phase, still owed to the other plane
   int dC_prev = 0;          // centre
   unsigned dmask_prev = 0;  // neighbours (values in s_D)
@@ -331,6 +348,10 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
   for (unsigned phase = 0;; ++phase) {
     const int rpar = (int)(phase & 1u), wpar = rpar ^ 1;
     const int cur = rpar * 8, prev = wpar * 8;
+    if (asleep && (unsigned)d.age <= phase) {
+      asleep = false;
+      alive = true;
+    }
     SHX_T(0);
 #ifdef SHX_PHASE_TIMING
     if (phase == 100u && (tid & 31) == 0 && (gid >> 5) < 8192u) {
@@ -556,7 +577,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
       if (w < 8192u) { g_arrival[w] = ns; g_arrival_sm[w] = smid; }
     }
 #endif
-    const unsigned block_sum = (unsigned)__syncthreads_count(alive || (dC_prev | (int)dmask_prev));
+    const unsigned block_sum = (unsigned)__syncthreads_count(alive || asleep || (dC_prev | (int)dmask_prev));
     SHX_T(5);
     const unsigned total = kPeer ? peer_barrier_sum(a.bar, a.pv, phase, block_sum, &s_total, &s_remote, bar_hi0, bar_hi1)
                                  : grid_barrier_sum(a.bar, phase, block_sum, &s_total, bar_hi0, bar_hi1);

@@ -33,6 +33,7 @@ class StripExchange:
         self.lo = rank - 1 if rank > 0 else None
         self.hi = rank + 1 if rank < world - 1 else None
         self.rounds = 0
+        self.carry = None  # erode_cycle: migrants received at the end of the previous call
 
     def _swap(self, to_lo, to_hi, like_lo, like_hi):
         """send to_lo/to_hi to the neighbours, receive same-shaped tensors from them"""
@@ -100,6 +101,30 @@ class StripExchange:
             self.b.run_drops(received)
         self.b.end()
 
+    # -- one exchange per call ("exchanged each cycle"): strips run a whole call independently
+    def erode_cycle(self, cycles, seed=0):
+        """World::erode with ONE exchange: every strip marches its own drops (plus the ones handed
+        over at the end of the previous call) to the end, then halo deltas / boundary rows / migrants
+        are exchanged once.  A drop that crosses a strip border pauses until the next call, where it
+        sleeps until the phase equal to its age (so it meets other drops at the same ages as in an
+        unsplit run instead of bunching up at phase 0).  No collective, no host-side loop: the strips
+        only meet their neighbours once per call.  erode_cycle(0) marches what is waiting without
+        spawning (end of a run: repeat until in_flight() == 0)."""
+        self.b.begin(cycles, seed, self.carry)
+        self.b.end()  # EMA of the owned rows: nothing below touches the records
+        self.exchange_heights()
+        self.carry = self.exchange_drops()
+        self.rounds = 1
+
+    def in_flight(self):
+        """drops waiting for the next call, summed over ranks"""
+        n = 0 if self.carry is None else self.carry.shape[0]
+        if self.world > 1:
+            t = torch.tensor([n], dtype=torch.int64, device=self.carry.device if self.carry is not None else None)
+            dist.all_reduce(t)
+            n = int(t.item())
+        return n
+
 
 class LocalStripSet:
     """k strips held by ONE process (e.g. k logical strips on one GPU): the same protocol as
@@ -109,6 +134,7 @@ class LocalStripSet:
     def __init__(self, backends):
         self.b = list(backends)
         self.rounds = 0
+        self.carry = None
 
     def _exchange_heights(self):
         k = len(self.b)
@@ -148,6 +174,34 @@ class LocalStripSet:
         for b in self.b:
             b.end()
 
+    def _route(self, outs):
+        k = len(self.b)
+        inbox = []
+        for i in range(k):
+            parts = []
+            if i > 0 and outs[i - 1][1].shape[0]:
+                parts.append(outs[i - 1][1])
+            if i < k - 1 and outs[i + 1][0].shape[0]:
+                parts.append(outs[i + 1][0])
+            inbox.append(torch.cat(parts) if parts else outs[i][0][:0].clone())
+        return inbox
+
+    def erode_cycle(self, cycles, seed=0):
+        """StripExchange.erode_cycle for k strips in one process"""
+        if self.carry is None:
+            self.carry = [None] * len(self.b)
+        for b, c in zip(self.b, self.carry):
+            b.begin(cycles, seed, c)
+            b.end()
+        self._exchange_heights()
+        outs = [b.pack_migrants() for b in self.b]
+        outs = [(lo.clone(), hi.clone()) for lo, hi in outs]
+        self.carry = self._route(outs)
+        self.rounds = 1
+
+    def in_flight(self):
+        return 0 if self.carry is None else sum(c.shape[0] for c in self.carry if c is not None)
+
 
 class GpuStrip:
     """backend over libshx: one strip context on one CUDA device, buffers are torch CUDA tensors"""
@@ -166,7 +220,7 @@ class GpuStrip:
         self.dev = torch.device("cuda", device)
         whole = world == 1
         nodes = (tiles // world) * tiles
-        self.cap = max(4096, nodes * drops_per_node)
+        self.cap = max(4096, 2 * nodes * drops_per_node)  # spawned + carried-over drops
         self.W = shx.World(params=p, device=device, row0=0 if whole else self.row0, row1=0 if whole else self.row1, halo=halo,
                            max_drops=self.cap)
         self.has_lo, self.has_hi = rank > 0, rank < world - 1
@@ -181,8 +235,12 @@ class GpuStrip:
     def _p(t):
         return t.data_ptr() if t is not None else None
 
-    def begin(self, cycles, seed):
-        self.W.strip_erode_begin(cycles, seed)
+    def begin(self, cycles, seed, carried=None):
+        if carried is not None and carried.shape[0]:
+            carried = carried.contiguous()
+            self.W.strip_erode_begin(cycles, seed, carried.data_ptr(), carried.shape[0])
+        else:
+            self.W.strip_erode_begin(cycles, seed)
 
     def end(self):
         self.W.strip_erode_end()

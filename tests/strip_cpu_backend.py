@@ -39,7 +39,7 @@ class CpuStrip:
         for n, _ in orc.Stats._fields_:
             setattr(self.stats, n, getattr(self.stats, n) + getattr(st, n))
 
-    def begin(self, cycles, seed):
+    def begin(self, cycles, seed, carried=None):
         self.stats = orc.Stats()
         self.ls.reset_tracks()
         xy = self.ls.spawn(seed, self.epoch, cycles)
@@ -47,7 +47,11 @@ class CpuStrip:
         mine = xy[(xy[:, 0] >= self.row0) & (xy[:, 0] < self.row1)]
         drops, st = self.ls.make_drops(mine)
         self._accumulate(st)
+        if carried is not None and carried.shape[0]:  # shx_strip_erode_begin_with: appended to the spawned batch
+            drops = np.concatenate([drops, carried.numpy().reshape(-1, 8).copy().view(orc.DROP_DTYPE).reshape(-1)])
+            self.ls.w.contents.align_age = 1  # carried drops wait for the phase equal to their age
         st, _ = self.ls.run_drops(drops)
+        self.ls.w.contents.align_age = 0
         self._accumulate(st)
         self.last = drops
 

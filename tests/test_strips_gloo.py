@@ -39,7 +39,7 @@ def free_port():
     return port
 
 
-def worker(rank, world, port, out_dir):
+def worker(rank, world, port, out_dir, mode="rounds"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     p, cells = make_world()
@@ -48,11 +48,24 @@ def worker(rank, world, port, out_dir):
     before = b.owned_height_sum()
     tot = orc.Stats()
     rounds = []
-    for c in range(NCYC):
-        ex.erode(CYCLES, seed=11)
-        rounds.append(ex.rounds)
+    def accumulate():
         for n, _ in orc.Stats._fields_:
             setattr(tot, n, getattr(tot, n) + getattr(b.stats, n))
+
+    for c in range(NCYC):
+        if mode == "cycle":  # one exchange per call; border crossers join the next call's batch
+            ex.erode_cycle(CYCLES, seed=11)
+            rounds.append(ex.rounds)
+        else:
+            ex.erode(CYCLES, seed=11)
+            rounds.append(ex.rounds)
+        accumulate()
+    if mode == "cycle":  # march what is still waiting, so that every drop is accounted for
+        assert ex.in_flight() > 0
+        while ex.in_flight():
+            ex.erode_cycle(0, seed=11)
+            accumulate()
+            rounds[-1] += 1
     after = b.owned_height_sum()
     # halos must equal the owner's rows after the last exchange: ship my edge rows to the neighbours
     lo, hi = b.pack_boundary()
@@ -71,17 +84,17 @@ def worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def run(world, tmp_path):
+def run(world, tmp_path, mode="rounds"):
     port = free_port()
-    mp.spawn(worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(worker, args=(world, port, str(tmp_path), mode), nprocs=world, join=True)
     parts = [np.load(os.path.join(tmp_path, f"rank{r}.npz")) for r in range(world)]
     return (np.concatenate([q["h"] for q in parts]), np.concatenate([q["field"] for q in parts]),
             np.stack([q["ledger"] for q in parts]))
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_strip_exchange_conserves_and_accounts(world, tmp_path):
-    h, field, led = run(world, tmp_path)
+@pytest.mark.parametrize("world,mode", [(2, "rounds"), (4, "rounds"), (2, "cycle"), (4, "cycle")])
+def test_strip_exchange_conserves_and_accounts(world, mode, tmp_path):
+    h, field, led = run(world, tmp_path, mode)
     assert led[:, 0].sum() == led[:, 1].sum()          # integer mass ledger over the union of strips: exact
     assert led[:, 2].sum() == led[:, 3].sum()          # every spawned drop terminated somewhere
     assert led[:, 2].sum() > 0.9 * MS * MS * CYCLES * NCYC
@@ -90,7 +103,7 @@ def test_strip_exchange_conserves_and_accounts(world, tmp_path):
     # deterministic
     d = tmp_path / "again"
     d.mkdir()
-    h2, field2, led2 = run(world, d)
+    h2, field2, led2 = run(world, d, mode)
     assert np.array_equal(h, h2) and np.array_equal(field.view(np.uint32), field2.view(np.uint32)) and np.array_equal(led, led2)
     # statistically the same world as the single-domain lock-step run
     p, cells = make_world()
