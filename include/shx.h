@@ -220,6 +220,17 @@ int shx_strip_set_halo(shx_ctx* c, const int32_t* dev_lo, const int32_t* dev_hi)
 /* drops that left the strip during the last run: compacted into dev_lo/dev_hi (capacity cap each);
  * counts are written to the two host ints (syncs) */
 int shx_strip_pack_migrants(shx_ctx* c, shx_drop* dev_lo, shx_drop* dev_hi, size_t cap, int* n_lo, int* n_hi);
+/* Strips that exchange ONCE per call: one message per neighbour, int32 words
+ *   [0] number of drop records  [1..7] unused  [8, 8+8*cap) drop records (shx_drop)
+ *   then halo*size halo deltas, then halo*size current edge rows.
+ * pack writes both outgoing messages (device buffers of shx_strip_message_words() words; a count
+ * above cap means records were lost: the receiver must treat it as SHX_ERR_CAPACITY); apply takes
+ * the neighbours' messages: their deltas onto the owned edge rows, and the halo copy becomes what
+ * the neighbour holds after taking this strip's deltas.  Neither call synchronises.  The drop
+ * records of the received messages go to the next shx_strip_erode_begin_with. */
+size_t shx_strip_message_words(const shx_ctx* c, size_t cap);
+int shx_strip_pack_message(shx_ctx* c, int32_t* dev_lo, int32_t* dev_hi, size_t cap);
+int shx_strip_apply_message(shx_ctx* c, const int32_t* dev_from_lo, const int32_t* dev_from_hi, size_t cap);
 /* continue drops received from neighbours (device buffer) until they finish or leave again */
 int shx_strip_run_device_drops(shx_ctx* c, const shx_drop* dev_drops, size_t n, shx_stats* out);
 /* one strip's share of World::erode split around the exchange rounds:

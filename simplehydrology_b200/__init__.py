@@ -122,6 +122,10 @@ def lib():
     L.shx_strip_pack_migrants.argtypes = [vp, vp, vp, sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.shx_strip_run_device_drops.argtypes = [vp, vp, sz, C.POINTER(Stats)]
     L.shx_strip_erode_begin.argtypes = [vp, C.c_int, u64]
+    L.shx_strip_message_words.argtypes = [vp, sz]
+    L.shx_strip_message_words.restype = sz
+    L.shx_strip_pack_message.argtypes = [vp, vp, vp, sz]
+    L.shx_strip_apply_message.argtypes = [vp, vp, vp, sz]
     L.shx_strip_erode_begin_with.argtypes = [vp, C.c_int, u64, vp, sz]
     L.shx_strip_erode_end.argtypes = [vp]
     L.shx_peer_export.argtypes = [vp, C.POINTER(PeerHandles)]
@@ -314,6 +318,15 @@ class World:
         return a.value, b.value
 
     # -- peer mode: one world over the GPUs of a box
+    def strip_message_words(self, cap):
+        return int(self.L.shx_strip_message_words(self._h, cap))
+
+    def strip_pack_message(self, lo, hi, cap):
+        self._check(self.L.shx_strip_pack_message(self._h, lo, hi, cap))
+
+    def strip_apply_message(self, from_lo, from_hi, cap):
+        self._check(self.L.shx_strip_apply_message(self._h, from_lo, from_hi, cap))
+
     def peer_export(self):
         h = PeerHandles()
         self._check(self.L.shx_peer_export(self._h, C.byref(h)))

@@ -908,6 +908,53 @@ int shx_strip_pack_migrants(shx_ctx* c, shx_drop* dev_lo, shx_drop* dev_hi, size
   return SHX_OK;
 }
 
+size_t shx_strip_message_words(const shx_ctx* c, size_t cap) {
+  if (!c) return 0;
+  return (size_t)kMsgHeader + 8 * cap + 2 * (size_t)c->cfg.halo * c->size;
+}
+
+int shx_strip_pack_message(shx_ctx* c, int32_t* dev_lo, int32_t* dev_hi, size_t cap) {
+  int rc = strip_check(c);
+  if (rc) return rc;
+  const size_t band = (size_t)c->cfg.halo * c->size;
+  int32_t* msg[2] = {c->halo_lo ? dev_lo : nullptr, c->halo_hi ? dev_hi : nullptr};
+  for (int side = 0; side < 2; side++) {
+    if ((side == 0 ? c->halo_lo : c->halo_hi) && !msg[side]) return fail(SHX_ERR_ARG, "null message buffer for an existing neighbour");
+    if (!msg[side]) continue;
+    if ((side == 0 ? c->halo_lo : c->halo_hi) != c->cfg.halo) return fail(SHX_ERR_ARG, "messages need full halos");
+    CU(cudaMemsetAsync(msg[side], 0, kMsgHeader * sizeof(int32_t), c->stream));
+    int32_t* rows = msg[side] + kMsgHeader + 8 * cap;
+    strip_msg_rows_kernel<<<grid_for(c, band), 256, 0, c->stream>>>(c->m.hq + band_halo(c, side), c->d_halo_ref[side],
+                                                                   c->m.hq + band_edge(c, side, c->cfg.halo), rows, rows + band, band);
+    c->launches++;
+  }
+  if (c->last_n && (msg[0] || msg[1])) {
+    // a drop can only have left towards an existing neighbour; the other pointer is never written
+    strip_msg_migrants_kernel<<<grid_for(c, c->last_n), 256, 0, c->stream>>>(c->d_drops, (unsigned)c->last_n, msg[0] ? msg[0] : msg[1],
+                                                                           msg[1] ? msg[1] : msg[0], (unsigned)cap);
+    c->launches++;
+  }
+  CU(cudaGetLastError());
+  return SHX_OK;
+}
+
+int shx_strip_apply_message(shx_ctx* c, const int32_t* from_lo, const int32_t* from_hi, size_t cap) {
+  int rc = strip_check(c);
+  if (rc) return rc;
+  const size_t band = (size_t)c->cfg.halo * c->size;
+  const int32_t* msg[2] = {c->halo_lo ? from_lo : nullptr, c->halo_hi ? from_hi : nullptr};
+  for (int side = 0; side < 2; side++) {
+    if ((side == 0 ? c->halo_lo : c->halo_hi) && !msg[side]) return fail(SHX_ERR_ARG, "null message buffer for an existing neighbour");
+    if (!msg[side]) continue;
+    const int32_t* rows = msg[side] + kMsgHeader + 8 * cap;
+    strip_msg_apply_kernel<<<grid_for(c, band), 256, 0, c->stream>>>(c->m.hq + band_halo(c, side), c->d_halo_ref[side],
+                                                                    c->m.hq + band_edge(c, side, c->cfg.halo), rows, rows + band, band);
+    c->launches++;
+  }
+  CU(cudaGetLastError());
+  return SHX_OK;
+}
+
 int shx_strip_run_device_drops(shx_ctx* c, const shx_drop* dev_drops, size_t n, shx_stats* out) {
   int rc = strip_check(c);
   if (rc) return rc;

@@ -281,4 +281,44 @@ __global__ void strip_pack_migrants_kernel(const shx_drop* drops, unsigned n, sh
   }
 }
 
+
+// One message per neighbour and call (strips that exchange once per call), int32 words:
+//   [0] number of drop records   [1..7] unused   [8, 8 + 8*cap) drop records
+//   then rows*size halo deltas (what this strip moved into its copy of the neighbour's edge rows)
+//   then rows*size edge rows (what this strip's own edge rows hold now)
+constexpr int kMsgHeader = 8;
+__global__ void strip_msg_rows_kernel(const int2* halo, const int32_t* ref, const int2* edge, int32_t* out_delta, int32_t* out_edge,
+                                      size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    out_delta[i] = halo[i].x - ref[i];
+    out_edge[i] = edge[i].x;
+  }
+}
+__global__ void strip_msg_migrants_kernel(const shx_drop* drops, unsigned n, int32_t* msg_lo, int32_t* msg_hi, unsigned cap) {
+  for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    shx_drop d = drops[k];
+    if (d.flags & (SHX_DROP_MIGRATE_LO | SHX_DROP_MIGRATE_HI)) {
+      int32_t* msg = (d.flags & SHX_DROP_MIGRATE_LO) ? msg_lo : msg_hi;
+      const unsigned slot = (unsigned)atomicAdd(msg, 1);  // a count above cap tells the receiver that records were dropped
+      d.flags = (d.flags & ~(SHX_DROP_MIGRATE_LO | SHX_DROP_MIGRATE_HI)) | SHX_DROP_ALIVE;
+      if (slot < cap) reinterpret_cast<shx_drop*>(msg + kMsgHeader)[slot] = d;
+    }
+  }
+}
+// The owner's edge rows take the neighbour's deltas; this strip's copy of the neighbour's edge rows
+// becomes what the neighbour holds once IT has taken this strip's deltas: its rows as sent + ours.
+__global__ void strip_msg_apply_kernel(int2* halo, int32_t* ref, int2* edge, const int32_t* in_delta, const int32_t* in_edge, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int32_t v = in_edge[i] + (halo[i].x - ref[i]);
+    halo[i] = make_int2(v, v);
+    ref[i] = v;
+    const int32_t dv = in_delta[i];
+    if (dv) {
+      int2 c = edge[i];
+      c.x += dv; c.y += dv;
+      edge[i] = c;
+    }
+  }
+}
+
 }  // namespace shx

@@ -33,7 +33,8 @@ class StripExchange:
         self.lo = rank - 1 if rank > 0 else None
         self.hi = rank + 1 if rank < world - 1 else None
         self.rounds = 0
-        self.carry = None  # erode_cycle: migrants received at the end of the previous call
+        self.inbox = None  # erode_cycle: the neighbours' messages received at the end of the previous call
+        self._counts = None
 
     def _swap(self, to_lo, to_hi, like_lo, like_hi):
         """send to_lo/to_hi to the neighbours, receive same-shaped tensors from them"""
@@ -110,20 +111,75 @@ class StripExchange:
         unsplit run instead of bunching up at phase 0).  No collective, no host-side loop: the strips
         only meet their neighbours once per call.  erode_cycle(0) marches what is waiting without
         spawning (end of a run: repeat until in_flight() == 0)."""
-        self.b.begin(cycles, seed, self.carry)
+        self.b.begin(cycles, seed, self._take_carry())
         self.b.end()  # EMA of the owned rows: nothing below touches the records
-        self.exchange_heights()
-        self.carry = self.exchange_drops()
+        out_lo, out_hi = self.b.pack_message()
+        self.inbox = self._swap(out_lo, out_hi, out_lo, out_hi)  # ONE message per neighbour: migrants + halo deltas + edge rows
+        self.b.apply_message(*self.inbox)
+        self._counts = _MessageCounts(self.inbox)  # read by the next call (or in_flight), not now
         self.rounds = 1
+
+    def _take_carry(self):
+        """the drop records of the messages received at the end of the previous call, [n, 8] int32"""
+        if self.inbox is None:
+            return None
+        return _records(self.inbox, self._counts.get(), self.b.cap)
 
     def in_flight(self):
         """drops waiting for the next call, summed over ranks"""
-        n = 0 if self.carry is None else self.carry.shape[0]
+        n = sum(self._counts.get()) if self.inbox is not None else 0
         if self.world > 1:
-            t = torch.tensor([n], dtype=torch.int64, device=self.carry.device if self.carry is not None else None)
+            ref = next((m for m in (self.inbox or ()) if m is not None), None)
+            t = torch.tensor([n], dtype=torch.int64, device=ref.device if ref is not None else None)
             dist.all_reduce(t)
             n = int(t.item())
         return n
+
+
+MSG_HEADER = 8  # int32 words before the drop records of a strip message (include/shx.h)
+
+
+class _MessageCounts:
+    """the record counts in the headers of the two received messages, fetched without stalling the
+    stream: an asynchronous copy into pinned memory now, waited for when somebody needs the numbers
+    (by then the caller has long synchronised for its stats)"""
+
+    def __init__(self, inbox):
+        self.n = None
+        heads = [m[:1] for m in inbox if m is not None]
+        self.present = [m is not None for m in inbox]
+        self.event = None
+        if not heads:
+            self.n = (0, 0)
+            return
+        dev = torch.cat(heads)
+        if dev.is_cuda:
+            self.host = torch.empty(len(heads), dtype=torch.int32, pin_memory=True)
+            self.host.copy_(dev, non_blocking=True)
+            self.event = torch.cuda.Event()
+            self.event.record()
+        else:
+            self.host = dev.clone()
+
+    def get(self):
+        if self.n is None:
+            if self.event is not None:
+                self.event.synchronize()
+            vals = iter(self.host.tolist())
+            self.n = tuple(int(next(vals)) if p else 0 for p in self.present)
+        return self.n
+
+
+def _records(inbox, counts, cap):
+    parts = []
+    for m, n in zip(inbox, counts):
+        if n > cap:
+            raise RuntimeError(f"a neighbour handed over {n} drops, more than the message capacity {cap}")
+        if m is not None and n:
+            parts.append(m[MSG_HEADER:MSG_HEADER + 8 * n].view(-1, 8))
+    if not parts:
+        return None
+    return parts[0] if len(parts) == 1 else torch.cat(parts)
 
 
 class LocalStripSet:
@@ -134,7 +190,7 @@ class LocalStripSet:
     def __init__(self, backends):
         self.b = list(backends)
         self.rounds = 0
-        self.carry = None
+        self.inbox = None  # erode_cycle: per strip, the (lo, hi) messages received at the end of the previous call
 
     def _exchange_heights(self):
         k = len(self.b)
@@ -174,33 +230,29 @@ class LocalStripSet:
         for b in self.b:
             b.end()
 
-    def _route(self, outs):
-        k = len(self.b)
-        inbox = []
-        for i in range(k):
-            parts = []
-            if i > 0 and outs[i - 1][1].shape[0]:
-                parts.append(outs[i - 1][1])
-            if i < k - 1 and outs[i + 1][0].shape[0]:
-                parts.append(outs[i + 1][0])
-            inbox.append(torch.cat(parts) if parts else outs[i][0][:0].clone())
-        return inbox
-
     def erode_cycle(self, cycles, seed=0):
         """StripExchange.erode_cycle for k strips in one process"""
-        if self.carry is None:
-            self.carry = [None] * len(self.b)
-        for b, c in zip(self.b, self.carry):
-            b.begin(cycles, seed, c)
+        k = len(self.b)
+        if self.inbox is None:
+            self.inbox = [None] * k
+        for b, box in zip(self.b, self.inbox):
+            carried = None
+            if box is not None:
+                counts = tuple(int(m[0]) if m is not None else 0 for m in box)
+                carried = _records(box, counts, b.cap)
+            b.begin(cycles, seed, carried)
             b.end()
-        self._exchange_heights()
-        outs = [b.pack_migrants() for b in self.b]
-        outs = [(lo.clone(), hi.clone()) for lo, hi in outs]
-        self.carry = self._route(outs)
+        outs = [b.pack_message() for b in self.b]
+        outs = [(lo.clone() if lo is not None else None, hi.clone() if hi is not None else None) for lo, hi in outs]
+        self.inbox = [(outs[i - 1][1] if i > 0 else None, outs[i + 1][0] if i < k - 1 else None) for i in range(k)]
+        for b, box in zip(self.b, self.inbox):
+            b.apply_message(*box)
         self.rounds = 1
 
     def in_flight(self):
-        return 0 if self.carry is None else sum(c.shape[0] for c in self.carry if c is not None)
+        if self.inbox is None:
+            return 0
+        return sum(int(m[0]) for box in self.inbox if box is not None for m in box if m is not None)
 
 
 class GpuStrip:
@@ -229,6 +281,7 @@ class GpuStrip:
         self.d_lo, self.d_hi, self.b_lo, self.b_hi = mk(), mk(), mk(), mk()
         self.out_lo = torch.zeros((self.cap, 8), dtype=torch.int32, device=self.dev)
         self.out_hi = torch.zeros((self.cap, 8), dtype=torch.int32, device=self.dev)
+        self.msg = None
         self.W.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
 
     @staticmethod
@@ -258,6 +311,16 @@ class GpuStrip:
 
     def set_halo(self, lo, hi):
         self.W.strip_set_halo(self._p(lo), self._p(hi))
+
+    def pack_message(self):
+        if self.msg is None:
+            words = self.W.strip_message_words(self.cap)
+            self.msg = [torch.zeros(words, dtype=torch.int32, device=self.dev) if has else None for has in (self.has_lo, self.has_hi)]
+        self.W.strip_pack_message(self._p(self.msg[0]), self._p(self.msg[1]), self.cap)
+        return self.msg[0], self.msg[1]
+
+    def apply_message(self, from_lo, from_hi):
+        self.W.strip_apply_message(self._p(from_lo), self._p(from_hi), self.cap)
 
     def pack_migrants(self):
         n_lo, n_hi = self.W.strip_pack_migrants(self.out_lo.data_ptr(), self.out_hi.data_ptr(), self.cap)

@@ -18,6 +18,7 @@ class CpuStrip:
         self.row0, self.row1 = rank * rows, (rank + 1) * rows
         self.ls.w.contents.row0, self.ls.w.contents.row1 = self.row0, self.row1
         self.halo = halo
+        self.cap = 2048  # drop records per message
         self.has_lo, self.has_hi = rank > 0, rank < world - 1
         self.epoch = 0
         self.stats = orc.Stats()
@@ -95,6 +96,42 @@ class CpuStrip:
             sel["flags"] = (sel["flags"] & ~(orc.DROP_MIGRATE_LO | orc.DROP_MIGRATE_HI)) | orc.DROP_ALIVE
             out.append(torch.from_numpy(sel.view(np.int32).reshape(-1, 8).copy()))
         return out[0], out[1]
+
+    # -- one message per neighbour and call (shx_strip_pack_message / shx_strip_apply_message)
+    def pack_message(self):
+        h = self.ls.height_q(0)
+        mig = self.pack_migrants()
+        out = []
+        for side, has in ((0, self.has_lo), (1, self.has_hi)):
+            if not has:
+                out.append(None)
+                continue
+            n = mig[side].shape[0]
+            msg = np.zeros(8 + 8 * self.cap + 2 * self.halo * self.size, np.int32)
+            msg[0] = n
+            msg[8:8 + 8 * min(n, self.cap)] = mig[side].numpy().ravel()[:8 * self.cap]
+            rows = 8 + 8 * self.cap
+            band = self.halo * self.size
+            msg[rows:rows + band] = (h[self._halo_rows(side)] - self.ref[side]).ravel()
+            msg[rows + band:rows + 2 * band] = h[self._edge_rows(side)].ravel()
+            out.append(torch.from_numpy(msg))
+        return out[0], out[1]
+
+    def apply_message(self, from_lo, from_hi):
+        rows = 8 + 8 * self.cap
+        band = self.halo * self.size
+        for side, t in ((0, from_lo), (1, from_hi)):
+            if t is None:
+                continue
+            m = t.numpy()
+            delta = m[rows:rows + band].reshape(self.halo, self.size)
+            edge = m[rows + band:rows + 2 * band].reshape(self.halo, self.size)
+            mine = self.ls.height_q(0)[self._halo_rows(side)] - self.ref[side]
+            v = edge + mine
+            for plane in (0, 1):
+                self.ls.height_q(plane)[self._halo_rows(side)] = v
+                self.ls.height_q(plane)[self._edge_rows(side)] += delta
+            self.ref[side] = v.copy()
 
     def run_drops(self, records):
         drops = records.numpy().reshape(-1, 8).copy().view(orc.DROP_DTYPE).reshape(-1)

