@@ -265,6 +265,28 @@ def run_cuda(args):
             if not peer:
                 line["exchange_rounds_per_cycle"] = rounds / max(args.steps, 1)
 
+    # ---- the per-frame consumers that follow erode in the reference's loop, as device
+    # kernels on the resident world: vertex fill (updatenode) and the discharge / momentum maps
+    own = (strip.row1 - strip.row0) * 512 * MAPSIZE
+    views = {}
+    for name, words, nbytes in (("vertex_fill", 12, 52), ("view_maps", 4, 36)):
+        buf = torch.empty(own * words, dtype=torch.float32, device=dev)
+        fn = (lambda: W.vertex_fill(buf.data_ptr())) if name == "vertex_fill" else (lambda: W.view_maps(buf.data_ptr()))
+        for _ in range(3):
+            fn()
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        v0.record()
+        for _ in range(5):
+            fn()
+        v1.record()
+        torch.cuda.synchronize()
+        vms = v0.elapsed_time(v1) / 5
+        views[name] = {"ms_per_launch": vms, "achieved": own * nbytes / (vms * 1e-3) / 1e9, "frac": own * nbytes / (vms * 1e-3) / 1e9 / peaks()[0],
+                       "algorithmic_bytes_per_cell": nbytes}
+        del buf
+    if rank == 0:
+        line["roofline"]["view_kernels"] = views
+
     # ---- e2e: the calls the host adaptor makes, with host buffers; with strips every rank downloads
     # its own rows into its own (whole-map sized, as the reference's) pool
     pool = np.zeros(cells, shx.CELL_DTYPE)

@@ -208,6 +208,20 @@ int shx_synth_terrain(shx_ctx* c, uint32_t seed);
 int shx_download_raw(shx_ctx* c, int32_t* hq2, void* rec32);
 int shx_stored_rows(const shx_ctx* c, int* xlo, int* nrows);
 
+/* ---- per-frame consumers of the eroded map, run on the device instead of the host
+ * shx_vertex_fill replaces the `updatenode(vertexpool, node)` loop (SimpleHydrology.cpp:322-324,
+ * source/cellpool.h:286-305): 12 floats per owned cell {position, normal, tangent, bitangent}
+ * (the 48-byte Vertex of source/vertexpool.h:6-26) in pool order, written to DEVICE memory --
+ * e.g. the vertex pool's VBO mapped with cudaGraphicsResourceGetMappedPointer -- so the interactive
+ * path needs no height download.  shx_vertex_download is the same into a host buffer.
+ * shx_view_maps replaces the dischargeMap / momentumMap builders (SimpleHydrology.cpp:341-354):
+ * 4 floats per owned cell in map order (x*size + y):
+ *   {erf(0.4*discharge), 0.5*(1+erf(momentumx)), 0.5*(1+erf(momentumy)), height}. */
+int shx_vertex_fill(shx_ctx* c, float* dev_out);
+int shx_vertex_download(shx_ctx* c, float* host_out, size_t ncells);
+int shx_view_maps(shx_ctx* c, float* dev_out);
+int shx_view_maps_download(shx_ctx* c, float* host_out, size_t ncells);
+
 /* ---- row-strip exchange (multi-GPU): buffers are DEVICE pointers owned by the caller
  * (e.g. torch tensors); the transport between ranks is the caller's (NCCL send/recv or P2P). */
 /* height deltas this strip accumulated in its halo rows since the last refresh: `halo`*size int32 per side */

@@ -757,3 +757,60 @@ void orc_fill_tiled_from_planar(const orc_params* p, const float* planar, orc_ce
       c->height = planar[(size_t)x * size + y];
     }
 }
+
+/* ---- per-frame views ------------------------------------------------------------------------ */
+
+/* node::height (cellpool.h:237-241): 0 outside the node */
+static float node_height(const orc_cell* node, int ts, int lx, int ly) {
+  if (lx < 0 || ly < 0 || lx >= ts || ly >= ts) return 0.0f;
+  return node[(size_t)lx * ts + ly].height;
+}
+
+/* cellpool.h:286-305.  glm semantics as in orc_seq_normal: cross products written out, normalize =
+ * v * (1/sqrt(dot(v,v))). */
+void orc_vertex_fill(const orc_params* p, const orc_cell* tiled, float* out) {
+  const int ts = p->tilesize, ms = p->mapsize;
+  const float sc = (float)p->mapscale;
+  for (int node = 0; node < ms * ms; node++) {
+    const orc_cell* nd = tiled + (size_t)node * ts * ts;
+    const int x0 = (node / ms) * ts, y0 = (node % ms) * ts; /* cellpool.h:327-336 */
+    for (int lx = 0; lx < ts; lx++)
+      for (int ly = 0; ly < ts; ly++) {
+        float* v = out + 12 * ((size_t)node * ts * ts + (size_t)lx * ts + ly);
+        const float hc = node_height(nd, ts, lx, ly);
+        const float hxp = node_height(nd, ts, lx + 1, ly), hxm = node_height(nd, ts, lx - 1, ly);
+        const float hyp = node_height(nd, ts, lx, ly + 1), hym = node_height(nd, ts, lx, ly - 1);
+        const int xm = lx > 0, xp = lx < ts - 1, ym = ly > 0, yp = ly < ts - 1;
+        const float Bp = sc * (hxp - hc), Bm = sc * (hxm - hc), Ap = sc * (hyp - hc), Am = sc * (hym - hc);
+        float nx = 0.0f, ny = 0.0f, nz = 0.0f;
+        if (xp && yp) { nx += -Bp; ny += 1.0f; nz += -Ap; } /* cellpool.h:187-188 */
+        if (xm && ym) { nx += Bm; ny += 1.0f; nz += Am; }   /* :190-191 */
+        if (xp && ym) { nx += -Bp; ny += 1.0f; nz += Am; }  /* :194-195 */
+        if (xm && yp) { nx += Bm; ny += 1.0f; nz += -Ap; }  /* :197-198 */
+        const float l2 = nx * nx + ny * ny + nz * nz;
+        if (sqrtf(l2) > 0.0f) { /* :200-201 */
+          const float inv = 1.0f / sqrtf(l2);
+          nx *= inv; ny *= inv; nz *= inv;
+        }
+        const float px = (float)(x0 + lx), pz = (float)(y0 + ly), py = sc * hc; /* :290-294 */
+        v[0] = px; v[1] = py; v[2] = pz;
+        v[3] = nx; v[4] = ny; v[5] = nz;
+        v[6] = (float)(x0 + lx + 1) - px; v[7] = sc * hxp - py; v[8] = pz - pz; /* T - P, :295,300 */
+        v[9] = px - px; v[10] = sc * hyp - py; v[11] = (float)(y0 + ly + 1) - pz; /* B - P, :296,301 */
+      }
+  }
+}
+
+/* SimpleHydrology.cpp:341-354 (values before TinyEngine packs them into bytes) */
+void orc_view_maps(const orc_params* p, const orc_cell* tiled, int erf_poly, float* out) {
+  const int size = p->tilesize * p->mapsize;
+  for (int x = 0; x < size; x++)
+    for (int y = 0; y < size; y++) {
+      const orc_cell* c = tiled + orc_tiled_index(p, x, y);
+      float* o = out + 4 * ((size_t)x * size + y);
+      o[0] = erf_poly ? orc_erff_poly(0.4f * c->discharge) : orc_erff_libm(0.4f * c->discharge); /* cellpool.h:242-244 */
+      o[1] = 0.5f * (1.0f + (erf_poly ? orc_erff_poly(c->momentumx) : orc_erff_libm(c->momentumx)));
+      o[2] = 0.5f * (1.0f + (erf_poly ? orc_erff_poly(c->momentumy) : orc_erff_libm(c->momentumy)));
+      o[3] = c->height;
+    }
+}

@@ -145,6 +145,12 @@ void orc_ls_erode_spawnlist(orc_ls_world* w, const float* xy, size_t n, orc_stat
 /* ---- synthetic seeded terrain (value-noise fBm, normalised to [0,1]); planar x*size+y */
 void orc_synth_terrain(float* height, int size, uint32_t seed);
 /* planar -> tiled AoS heights (other fields zero) */
+/* quad::updatenode over every node (cellpool.h:286-305): 12 floats per cell {position, normal, tangent,
+ * bitangent} in pool order, from the tiled AoS cells; node-local height()/normal() as in the reference */
+void orc_vertex_fill(const orc_params* p, const orc_cell* tiled, float* out);
+/* dischargeMap / momentumMap values (SimpleHydrology.cpp:341-354) + height, 4 floats per cell in map
+ * order (x*size + y); erf_poly as in orc_seq_world */
+void orc_view_maps(const orc_params* p, const orc_cell* tiled, int erf_poly, float* out);
 void orc_fill_tiled_from_planar(const orc_params* p, const float* planar, orc_cell* tiled);
 
 #ifdef __cplusplus

@@ -122,6 +122,10 @@ def lib():
     L.shx_strip_pack_migrants.argtypes = [vp, vp, vp, sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.shx_strip_run_device_drops.argtypes = [vp, vp, sz, C.POINTER(Stats)]
     L.shx_strip_erode_begin.argtypes = [vp, C.c_int, u64]
+    L.shx_vertex_fill.argtypes = [vp, vp]
+    L.shx_vertex_download.argtypes = [vp, vp, sz]
+    L.shx_view_maps.argtypes = [vp, vp]
+    L.shx_view_maps_download.argtypes = [vp, vp, sz]
     L.shx_strip_message_words.argtypes = [vp, sz]
     L.shx_strip_message_words.restype = sz
     L.shx_strip_pack_message.argtypes = [vp, vp, vp, sz]
@@ -318,6 +322,32 @@ class World:
         return a.value, b.value
 
     # -- peer mode: one world over the GPUs of a box
+    # -- per-frame views (cellpool.h:286-305, SimpleHydrology.cpp:341-354)
+    def owned_cells(self):
+        r0, r1 = (self.cfg.row0, self.cfg.row1) if self.cfg.row1 else (0, self.size)
+        if self.cfg.peer_world > 1:
+            rows = self.size // self.cfg.peer_world
+            r0, r1 = self.cfg.peer_rank * rows, (self.cfg.peer_rank + 1) * rows
+        return (r1 - r0) * self.size
+
+    def vertex_fill(self, dev_ptr):
+        self._check(self.L.shx_vertex_fill(self._h, dev_ptr))
+
+    def vertex_download(self):
+        n = self.owned_cells()
+        out = np.zeros((n, 12), np.float32)
+        self._check(self.L.shx_vertex_download(self._h, out.ctypes.data, n))
+        return out
+
+    def view_maps(self, dev_ptr):
+        self._check(self.L.shx_view_maps(self._h, dev_ptr))
+
+    def view_maps_download(self):
+        n = self.owned_cells()
+        out = np.zeros((n, 4), np.float32)
+        self._check(self.L.shx_view_maps_download(self._h, out.ctypes.data, n))
+        return out
+
     def strip_message_words(self, cap):
         return int(self.L.shx_strip_message_words(self._h, cap))
 

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "shx_kernels.cuh"
+#include "shx_view_kernels.cuh"
 
 struct LaunchShape {
   const void* kernel = nullptr;
@@ -47,6 +48,8 @@ struct shx_ctx {
   int size = 0;
   MapView m{};
   size_t stored_cells = 0, owned_cells = 0;
+  float* d_view = nullptr;  // staging for shx_vertex_download / shx_view_maps_download (allocated on first use)
+  size_t view_bytes = 0;
   int halo_lo = 0, halo_hi = 0;  // halo rows actually present on each side
   shx_drop* d_drops = nullptr;
   size_t max_drops = 0;
@@ -163,6 +166,7 @@ void shx_destroy(shx_ctx* c) {
   for (void* p : c->peer_opened)
     if (p) cudaIpcCloseMemHandle(p);
   cudaFree(c->d_inbox);
+  cudaFree(c->d_view);
   if (c->h_stats) cudaFreeHost(c->h_stats);
   if (c->h_flags) cudaFreeHost(c->h_flags);
   delete c;
@@ -458,6 +462,76 @@ int shx_download_raw(shx_ctx* c, int32_t* hq2, void* rec32) {
   CU(cudaStreamSynchronize(c->stream));
   if (hq2) CU(cudaMemcpy(hq2, c->m.hq, c->stored_cells * sizeof(int2), cudaMemcpyDeviceToHost));
   if (rec32) CU(cudaMemcpy(rec32, c->m.rec, c->stored_cells * sizeof(CellRec), cudaMemcpyDeviceToHost));
+  return SHX_OK;
+}
+
+// ------------------------------------------------------------------------------- per-frame views
+
+static ViewArgs view_args(const shx_ctx* c) {
+  ViewArgs a;
+  a.m = c->m;
+  a.tilesize = c->p.tilesize;
+  a.mapsize = c->p.mapsize;
+  a.sequential = sequential(c) ? 1 : 0;
+  a.mapscale = c->p.mapscale;
+  return a;
+}
+
+static int view_staging(shx_ctx* c, size_t bytes) {
+  if (c->view_bytes >= bytes) return SHX_OK;
+  cudaFree(c->d_view);
+  c->d_view = nullptr;
+  c->view_bytes = 0;
+  if (cudaMalloc((void**)&c->d_view, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(SHX_ERR_NOMEM, "cudaMalloc failed for the view staging buffer");
+  }
+  c->view_bytes = bytes;
+  return SHX_OK;
+}
+
+int shx_vertex_fill(shx_ctx* c, float* dev_out) {  // cellpool.h:286-305 over every owned node
+  if (!c || !dev_out) return fail(SHX_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->cfg.device));
+  const int ts = c->p.tilesize;
+  if (c->m.row0 % ts || c->m.row1 % ts) return fail(SHX_ERR_ARG, "vertex fill needs tile-aligned strips");
+  const size_t first = (size_t)(c->m.row0 / ts) * c->p.mapsize * ts * ts;
+  const int grid = (int)std::min<size_t>((c->owned_cells + 255) / 256, (size_t)c->sm_count * 16);
+  vertex_fill_kernel<<<grid, 256, 0, c->stream>>>(view_args(c), dev_out, c->owned_cells, first);
+  c->launches++;
+  CU(cudaGetLastError());
+  return SHX_OK;
+}
+
+int shx_vertex_download(shx_ctx* c, float* host_out, size_t ncells) {
+  if (!c || !host_out) return fail(SHX_ERR_ARG, "null argument");
+  if (ncells != c->owned_cells) return fail(SHX_ERR_ARG, "vertex buffer must hold the owned cells");
+  int rc = view_staging(c, c->owned_cells * 12 * sizeof(float));
+  if (rc) return rc;
+  if ((rc = shx_vertex_fill(c, c->d_view))) return rc;
+  CU(cudaMemcpyAsync(host_out, c->d_view, c->owned_cells * 12 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return SHX_OK;
+}
+
+int shx_view_maps(shx_ctx* c, float* dev_out) {  // SimpleHydrology.cpp:341-354
+  if (!c || !dev_out) return fail(SHX_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->cfg.device));
+  const int grid = (int)std::min<size_t>((c->owned_cells + 255) / 256, (size_t)c->sm_count * 16);
+  view_maps_kernel<<<grid, 256, 0, c->stream>>>(view_args(c), reinterpret_cast<float4*>(dev_out), c->owned_cells);
+  c->launches++;
+  CU(cudaGetLastError());
+  return SHX_OK;
+}
+
+int shx_view_maps_download(shx_ctx* c, float* host_out, size_t ncells) {
+  if (!c || !host_out) return fail(SHX_ERR_ARG, "null argument");
+  if (ncells != c->owned_cells) return fail(SHX_ERR_ARG, "map buffer must hold the owned cells");
+  int rc = view_staging(c, c->owned_cells * 4 * sizeof(float));
+  if (rc) return rc;
+  if ((rc = shx_view_maps(c, c->d_view))) return rc;
+  CU(cudaMemcpyAsync(host_out, c->d_view, c->owned_cells * 4 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   return SHX_OK;
 }
 

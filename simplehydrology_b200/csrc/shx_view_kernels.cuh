@@ -1,0 +1,92 @@
+// Per-frame consumers of the eroded map that the reference runs on the host right after
+// World::erode (SimpleHydrology.cpp:322-324, 341-354), as streaming kernels over the device map:
+//   vertex_fill_kernel   quad::updatenode  (source/cellpool.h:286-305)  -> 48-byte Vertex records
+//   view_maps_kernel     dischargeMap / momentumMap builders (SimpleHydrology.cpp:341-354)
+// Both are HBM-bound (one pass over the heights / fields, one coalesced write of the result).
+#pragma once
+#include "shx_kernels.cuh"
+
+namespace shx {
+
+struct ViewArgs {
+  MapView m;
+  int tilesize, mapsize;  // cells per tile side, tiles per map side
+  int sequential;         // heights are fp32 bit patterns instead of Q5.26
+  float mapscale;
+};
+
+__device__ __forceinline__ float view_height(const ViewArgs& a, int x, int y) {
+  const int2 v = __ldg(a.m.hq + (size_t)(x - a.m.xlo) * a.m.size + y);
+  return a.sequential ? __int_as_float(v.x) : h_to_float(v.x);
+}
+
+// quad::updatenode for every node of the owned rows.  out: 12 floats per cell {position, normal,
+// tangent, bitangent} (vertexpool.h:6-26) in pool order: node (x/ts)*mapsize + (y/ts), then
+// x*ts + y inside the node -- the order of the reference's vertex pool sections.  Everything is
+// NODE-local like the reference: node::height() of a cell outside the node is 0 and node::normal()
+// only uses the planes whose corner lies inside the node (cellpool.h:227-250).
+// One thread per cell; the block's records go through shared memory so that the 48-byte records
+// leave as full 16-byte-per-lane coalesced stores.
+__global__ void __launch_bounds__(256) vertex_fill_kernel(const ViewArgs a, float* __restrict__ out, const size_t ncells,
+                                                          const size_t first_cell) {
+  __shared__ __align__(16) float s_v[256 * 12];
+  const int ts = a.tilesize, ta = ts * ts;
+  for (size_t base = (size_t)blockIdx.x * 256; base < ncells; base += (size_t)gridDim.x * 256) {
+    const size_t i = base + threadIdx.x;
+    if (i < ncells) {
+      const size_t g = first_cell + i;  // index in the pool of the whole map
+      const int node = (int)(g / ta), r = (int)(g % ta);
+      const int lx = r / ts, ly = r % ts;
+      const int x = (node / a.mapsize) * ts + lx, y = (node % a.mapsize) * ts + ly;
+      const bool xm = lx > 0, xp = lx < ts - 1, ym = ly > 0, yp = ly < ts - 1;
+      const float hc = view_height(a, x, y);
+      const float hxp = xp ? view_height(a, x + 1, y) : 0.0f;
+      const float hxm = xm ? view_height(a, x - 1, y) : 0.0f;
+      const float hyp = yp ? view_height(a, x, y + 1) : 0.0f;
+      const float hym = ym ? view_height(a, x, y - 1) : 0.0f;
+      // cellpool.h:181-204, the four cross products written out (see shx_step.cuh move_math)
+      const float Bp = a.mapscale * (hxp - hc), Bm = a.mapscale * (hxm - hc);
+      const float Ap = a.mapscale * (hyp - hc), Am = a.mapscale * (hym - hc);
+      float nx = 0.0f, ny = 0.0f, nz = 0.0f;
+      if (xp && yp) { nx += -Bp; ny += 1.0f; nz += -Ap; }
+      if (xm && ym) { nx += Bm; ny += 1.0f; nz += Am; }
+      if (xp && ym) { nx += -Bp; ny += 1.0f; nz += Am; }
+      if (xm && yp) { nx += Bm; ny += 1.0f; nz += -Ap; }
+      const float l2 = nx * nx + ny * ny + nz * nz;
+      if (l2 > 0.0f) {
+        const float inv = 1.0f / sqrtf(l2);
+        nx *= inv; ny *= inv; nz *= inv;
+      }
+      const float py = a.mapscale * hc;  // cellpool.h:294-296: P, T, B; T - P and B - P component-wise
+      // three 16-byte shared stores per thread at a 48-byte stride: conflict-free per quarter-warp
+      float4* v = reinterpret_cast<float4*>(s_v) + threadIdx.x * 3;
+      v[0] = make_float4((float)x, py, (float)y, nx);
+      v[1] = make_float4(ny, nz, (float)(x + 1) - (float)x, a.mapscale * hxp - py);
+      v[2] = make_float4(0.0f, 0.0f, a.mapscale * hyp - py, (float)(y + 1) - (float)y);
+    }
+    __syncthreads();
+    const size_t nblk = (ncells - base < 256 ? ncells - base : 256) * 3;  // float4s of this block
+    float4* dst = reinterpret_cast<float4*>(out + base * 12);
+    for (size_t k = threadIdx.x; k < nblk; k += 256) dst[k] = reinterpret_cast<const float4*>(s_v)[k];
+    __syncthreads();
+  }
+}
+
+// dischargeMap alpha = erf(0.4f*discharge) (cellpool.h:242-244 via :439) and momentumMap
+// {0.5*(1+erf(mx)), 0.5*(1+erf(my))} (SimpleHydrology.cpp:349-353), per cell of the owned rows in
+// map order (x*size + y).  out: float4 {discharge alpha, momentum r, momentum g, height}.
+__global__ void view_maps_kernel(const ViewArgs a, float4* __restrict__ out, const size_t ncells) {
+  const size_t off = (size_t)(a.m.row0 - a.m.xlo) * a.m.size;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncells; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 f = __ldg(reinterpret_cast<const float4*>(a.m.rec + off + i));  // discharge momentumx momentumy rootdensity
+    const int2 hv = __ldg(a.m.hq + off + i);
+    float4 o;
+    o.x = shx_erff(0.4f * f.x);
+    o.y = 0.5f * (1.0f + shx_erff(f.y));
+    o.z = 0.5f * (1.0f + shx_erff(f.z));
+    o.w = a.sequential ? __int_as_float(hv.x) : h_to_float(hv.x);
+    out[i] = o;
+  }
+}
+
+}  // namespace shx

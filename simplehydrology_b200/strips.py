@@ -258,7 +258,7 @@ class LocalStripSet:
 class GpuStrip:
     """backend over libshx: one strip context on one CUDA device, buffers are torch CUDA tensors"""
 
-    def __init__(self, mapsize, rank, world, device, halo=2, params=None, drops_per_node=512):
+    def __init__(self, mapsize, rank, world, device, halo=2, params=None, drops_per_node=512, **world_kw):
         import simplehydrology_b200 as shx
         self.shx = shx
         p = params if params is not None else shx.default_params(mapsize)
@@ -274,7 +274,7 @@ class GpuStrip:
         nodes = (tiles // world) * tiles
         self.cap = max(4096, 2 * nodes * drops_per_node)  # spawned + carried-over drops
         self.W = shx.World(params=p, device=device, row0=0 if whole else self.row0, row1=0 if whole else self.row1, halo=halo,
-                           max_drops=self.cap)
+                           max_drops=self.cap, **world_kw)
         self.has_lo, self.has_hi = rank > 0, rank < world - 1
         n = halo * size
         mk = lambda: torch.zeros(n, dtype=torch.int32, device=self.dev)

@@ -122,7 +122,23 @@ def part_cascade_kat():
     return {"cascade_cases": np.stack(cases), "cascade_after": np.stack(outs)}
 
 
-PARTS = {"world": part_world, "cycles": part_cycles, "stock": part_stock_erode, "cascade": part_cascade_kat}
+def part_vertices():
+    """quad::updatenode (cellpool.h:286-305) through the reference's Vertexpool::fill: fresh map and after one cycle"""
+    import orc
+    R = orc.Ref(1, seed=1)
+    rng = np.random.default_rng(77)
+    sample = np.concatenate([[0, 1, 511, 512, 513, 512 * 511, 512 * 512 - 1, 512 * 256 + 255],
+                             rng.integers(0, 512 * 512, 248)]).astype(np.int64)
+    out = {"vertex_sample_idx": sample}
+    for tag in ("fresh", "eroded"):
+        v = R.vertices() + np.float32(0.0)  # -0 -> +0: only the sign of a zero is not pinned
+        out[f"vertex_{tag}_sha"] = np.frombuffer(bytes.fromhex(sha(v)), np.uint8)
+        out[f"vertex_{tag}_sample"] = v[sample].copy()
+        R.erode_spawnlist(spawn_lists()[0])
+    return out
+
+
+PARTS = {"vertices": part_vertices, "world": part_world, "cycles": part_cycles, "stock": part_stock_erode, "cascade": part_cascade_kat}
 
 if __name__ == "__main__":
     if len(sys.argv) == 3 and sys.argv[1] == "--part":

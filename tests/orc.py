@@ -93,6 +93,8 @@ def lib():
         L.orc_ls_erode_spawnlist.argtypes = [C.POINTER(LsWorld), C.c_void_p, C.c_size_t, C.POINTER(Stats)]
         L.orc_synth_terrain.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
         L.orc_fill_tiled_from_planar.argtypes = [C.POINTER(Params), C.c_void_p, C.c_void_p]
+        L.orc_vertex_fill.argtypes = [C.POINTER(Params), C.c_void_p, C.c_void_p]
+        L.orc_view_maps.argtypes = [C.POINTER(Params), C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -123,6 +125,20 @@ def planar_to_tiled(p, planar_height):
 def tiled_to_planar(p, cells, field="height"):
     size = p.tilesize * p.mapsize
     return cells[field][tiled_index_map(p).ravel()].reshape(size, size)
+
+
+def vertex_fill(p, cells):
+    """quad::updatenode restated (oracle): [ncells, 12] float32 in pool order"""
+    out = np.zeros((cells.size, 12), np.float32)
+    lib().orc_vertex_fill(C.byref(p), cells.ctypes.data, out.ctypes.data)
+    return out
+
+
+def view_maps(p, cells, erf_poly=1):
+    """dischargeMap / momentumMap values + height: [size*size, 4] float32 in map order"""
+    out = np.zeros((cells.size, 4), np.float32)
+    lib().orc_view_maps(C.byref(p), cells.ctypes.data, int(erf_poly), out.ctypes.data)
+    return out
 
 
 def synth_terrain(size, seed):

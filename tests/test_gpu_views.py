@@ -1,0 +1,72 @@
+"""GPU: the per-frame consumers of the eroded map run on the device:
+shx_vertex_fill = quad::updatenode (cellpool.h:286-305), shx_view_maps = the dischargeMap /
+momentumMap builders (SimpleHydrology.cpp:341-354).  Checked against the committed reference
+vectors (tests/golden) and the oracle restatement; float equality (the sign of a zero is not pinned)."""
+import numpy as np
+import pytest
+import torch
+
+import orc
+import simplehydrology_b200 as shx
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def test_vertex_fill_matches_the_reference_vectors(golden, init_cells):
+    """sequential mode keeps fp32 heights: the Vertex records equal the reference's own (golden) bit for bit"""
+    with shx.World(mapsize=1, mode=shx.MODE_SEQUENTIAL) as W:
+        W.upload(init_cells)
+        v = W.vertex_download() + np.float32(0.0)
+        idx = golden["vertex_sample_idx"]
+        assert np.array_equal(bits(v[idx]), bits(golden["vertex_fresh_sample"]))
+        assert np.array_equal(bits(v), bits(orc.vertex_fill(orc.default_params(1), init_cells) + np.float32(0.0)))
+        W.erode_spawnlist(golden["spawn_lists"][0])
+        v = W.vertex_download() + np.float32(0.0)
+        assert np.array_equal(bits(v[idx]), bits(golden["vertex_eroded_sample"]))
+
+
+@pytest.mark.parametrize("mapsize", [1, 4])
+def test_vertex_fill_and_view_maps_after_batched_erosion(mapsize):
+    """batched mode: the kernels read the Q5.26 heights; the oracle gets the downloaded cells (same values)"""
+    p = shx.default_params(mapsize)
+    with shx.World(params=p) as W:
+        W.synth_terrain(3)
+        for _ in range(3):
+            W.erode(256, 7)
+        cells = W.download()
+        v = W.vertex_download()
+        m = W.view_maps_download()
+    po = orc.default_params(mapsize)
+    assert np.array_equal(v, orc.vertex_fill(po, cells))
+    want = orc.view_maps(po, cells, erf_poly=1)
+    assert np.array_equal(m, want)
+    # against libm's erf (what the reference calls) the kernels' polynomial stays within 2 ulp of 1
+    ref = orc.view_maps(po, cells, erf_poly=0)
+    assert np.abs(m - ref).max() <= 2.4e-7
+    assert m[:, 0].max() > 0.5  # rivers formed: discharge alpha is not trivially zero
+    n = v[:, 3:6]
+    assert np.allclose(np.linalg.norm(n, axis=1), 1.0, atol=1e-6)
+
+
+def test_vertex_fill_into_a_caller_owned_device_buffer_and_strips():
+    """the interop path: the caller hands a device pointer (a mapped VBO in the reference's renderer);
+    strips fill their own nodes and together give the whole pool"""
+    ms = 2
+    with shx.World(mapsize=ms) as W:
+        W.synth_terrain(5)
+        whole = W.vertex_download()
+        buf = torch.zeros(W.owned_cells() * 12, dtype=torch.float32, device="cuda")
+        W.set_stream(torch.cuda.current_stream().cuda_stream)
+        W.vertex_fill(buf.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(buf.cpu().numpy().reshape(-1, 12), whole)
+    parts = []
+    for r in range(2):
+        with shx.World(mapsize=ms, row0=r * 512, row1=(r + 1) * 512) as S:
+            S.synth_terrain(5)
+            parts.append(S.vertex_download())
+    assert np.array_equal(np.concatenate(parts), whole)

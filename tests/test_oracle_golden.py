@@ -162,3 +162,15 @@ def test_erf_restatement_accuracy():
     ulp = np.spacing(np.maximum(np.abs(want), 1e-30).astype(np.float32)).astype(np.float64)
     assert np.max(np.abs(got - want) / ulp) < 1.6  # tools/fit_erf.py: 1.47 ulp
     assert L.orc_erff_poly(0.0) == 0.0 and L.orc_erff_libm(0.0) == 0.0
+
+
+def test_vertex_fill_matches_reference_updatenode(golden, init_cells):
+    """quad::updatenode (cellpool.h:286-305): 48-byte Vertex records of the fresh map and after one erode cycle"""
+    cells = init_cells.copy()
+    p = orc.default_params(1)
+    S = orc.Seq(cells)
+    for tag in ("fresh", "eroded"):
+        v = orc.vertex_fill(p, cells) + np.float32(0.0)
+        assert np.array_equal(bits(v[golden["vertex_sample_idx"]]), bits(golden[f"vertex_{tag}_sample"])), tag
+        assert np.array_equal(sha(v), golden[f"vertex_{tag}_sha"]), tag
+        S.erode_spawnlist(golden["spawn_lists"][0])

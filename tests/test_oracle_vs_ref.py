@@ -68,3 +68,25 @@ ok &= np.array_equal(R.cells.view(np.uint8), cells.view(np.uint8))
 print("OK" if ok else "MISMATCH")
 """)
     assert out.strip().endswith("OK")
+
+
+VERTEX_SCRIPT = r"""
+import numpy as np, orc
+R = orc.Ref(%d, seed=1)
+rng = np.random.default_rng(5)
+ok = True
+for rounds in range(2):
+    a = R.vertices(); b = orc.vertex_fill(orc.default_params(%d), R.cells)
+    ok &= a.shape == b.shape and np.array_equal(a, b)      # float equality: only the sign of a zero may differ
+    ok &= float(np.abs(a[:, 3:6]).max()) <= 1.0 and a[:, 4].min() > 0.0
+    R.erode_spawnlist(rng.uniform(0, R.size - 1, size=(400, 2)).astype(np.float32))   # vertices of an eroded map too
+print("OK" if ok else "MISMATCH")
+"""
+
+
+@pytest.mark.parametrize("mapsize", [1, 4])
+def test_vertex_fill_restatement_matches_updatenode(mapsize):
+    """quad::updatenode (cellpool.h:286-305) through the reference's own Vertexpool::fill vs orc_vertex_fill"""
+    if not orc.have_ref(mapsize):
+        pytest.skip("oracle/_ref for this map size not built")
+    assert orc.run_ref_script(VERTEX_SCRIPT % (mapsize, mapsize)).strip().endswith("OK")
