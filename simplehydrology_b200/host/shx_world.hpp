@@ -90,6 +90,18 @@ class Bridge {
     for (size_t i = 0; i < ncells_; i++) root_shadow_[i] = pool_[i].rootdensity;
   }
 
+  // == `for (auto& node : world.map.nodes) updatenode(vertexpool, node);` (SimpleHydrology.cpp:322-324)
+  // on the device.  `vertices` receives the 48-byte Vertex records (vertexpool.h:6-26) of every
+  // cell in pool order, i.e. exactly what the reference's Vertexpool<Vertex>::fill calls leave in
+  // the pool's mapped buffer (sections are reserved node by node, cellpool.h:327-336).
+  void update_vertices(float* vertices) { check(shx_vertex_download(ctx_, vertices, ncells_), "shx_vertex_download"); }
+  // the same straight into device memory, e.g. the vertex pool's VBO registered with
+  // cudaGraphicsGLRegisterBuffer and mapped: no vertex data crosses PCIe
+  void update_vertices_device(float* dev_vertices) { check(shx_vertex_fill(ctx_, dev_vertices), "shx_vertex_fill"); }
+  // == the dischargeMap / momentumMap lambdas (SimpleHydrology.cpp:341-354): 4 floats per cell in
+  // map order {erf(0.4*discharge), 0.5*(1+erf(momentumx)), 0.5*(1+erf(momentumy)), height}
+  void view_maps(float* rgba) { check(shx_view_maps_download(ctx_, rgba, ncells_), "shx_view_maps_download"); }
+
   shx_ctx* context() { return ctx_; }
   const shx_params& params() const { return params_; }
 
