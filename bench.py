@@ -344,11 +344,11 @@ def run_cuda(args):
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "oracle/_ref not built"}
         except Exception as e:  # the baseline must never take the GPU numbers down with it
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"failed: {e}"}
-    if rank == 0:
-        print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0:  # last thing on stdout: NCCL may print its version banner whenever it first builds a communicator
+        print(json.dumps(line), flush=True)
     return 0
 
 
