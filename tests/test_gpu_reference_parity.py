@@ -125,3 +125,46 @@ def test_check3_statistical_parity_with_reference(init_cells):
     # bulk statistics of the eroded world
     assert abs(gpu["height"].mean(dtype=np.float64) - ref["height"].mean(dtype=np.float64)) < 2e-4
     assert abs(gpu["discharge"].sum(dtype=np.float64) / ref["discharge"].sum(dtype=np.float64) - 1) < 0.05
+
+
+def test_check3_row_strips_against_the_reference():
+    """The multi-GPU decomposition (4 row strips exchanging once per call, simplehydrology_b200/strips.py,
+    emulated on one device) against the reference's sequential loop on the same 2048^2 world and the same
+    spawn positions.  Stated bounds: RMSE within 1.15x of the reorder baseline (the reference against itself with its
+    drops processed in another order), correlations no more than 0.05 below it.  Measured on B200: baseline rmse
+    7.70e-4 corr 0.856 / 0.867; one domain 7.65e-4, 0.859 / 0.872; 4 strips 7.96e-4, 0.842 / 0.854."""
+    from simplehydrology_b200 import strips
+    ms, cyc, ncyc, seed, tseed = 4, 128, 5, 21, 3
+    p = orc.default_params(ms)
+    h0 = orc.synth_terrain(512 * ms, tseed)
+    init = orc.planar_to_tiled(p, h0)
+    with shx.World(mapsize=ms) as W:  # the spawn positions every variant uses (hash keyed by node: same for any k)
+        spawns = [W.spawn(cyc, seed, c) for c in range(ncyc)]
+        W.synth_terrain(tseed)
+        for c in range(ncyc):
+            W.erode(cyc, seed)
+        one = W.download()
+    ref, shuf = init.copy(), init.copy()
+    S, S2 = orc.Seq(ref, params=p), orc.Seq(shuf, params=p)
+    for c, xy in enumerate(spawns):
+        S.erode_spawnlist(xy)
+        S2.erode_spawnlist(xy[np.random.default_rng(500 + c).permutation(len(xy))])
+    k = 4
+    bs = [strips.GpuStrip(ms, r, k, 0) for r in range(k)]
+    for b in bs:
+        b.W.synth_terrain(tseed)
+    L = strips.LocalStripSet(bs)
+    for c in range(ncyc):
+        L.erode_cycle(cyc, seed)
+    parts = [b.W.download() for b in bs]  # each strip fills its own nodes of a whole-map pool
+    tiles_per_strip = (ms // k) * ms * 512 * 512
+    got = np.concatenate([q[r * tiles_per_strip:(r + 1) * tiles_per_strip] for r, q in enumerate(parts)])
+    for b in bs:
+        b.W.close()
+    rmse_b, corr_b, cdis_b = _metrics(ref, shuf, init)
+    rmse_1, corr_1, cdis_1 = _metrics(ref, one, init)
+    rmse_k, corr_k, cdis_k = _metrics(ref, got, init)
+    print(f"baseline rmse {rmse_b:.6f} corr {corr_b:.4f} cdis {cdis_b:.4f} | one domain rmse {rmse_1:.6f} corr {corr_1:.4f} cdis {cdis_1:.4f}"
+          f" | {k} strips rmse {rmse_k:.6f} corr {corr_k:.4f} cdis {cdis_k:.4f}")
+    assert rmse_1 <= 1.25 * rmse_b and corr_1 >= corr_b - 0.03 and cdis_1 >= cdis_b - 0.05
+    assert rmse_k <= 1.15 * rmse_b and corr_k >= corr_b - 0.05 and cdis_k >= cdis_b - 0.05
