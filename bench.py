@@ -321,6 +321,40 @@ def run_cuda(args):
         dist.all_reduce(tsum)
     shx.lib().shx_host_unregister(pool.ctypes.data)
     del pool
+
+    # ---- the same loop when the per-frame consumers run on the device: no pool download; the vertex records go
+    # into a device buffer (the renderer's VBO through interop) and the host reads back only the cells its
+    # vegetation pass looks at (shx_gather_cells).  Reported beside e2e, not instead of it.
+    vbuf = torch.empty(own * 12, dtype=torch.float32, device=dev)
+    nq = 8192
+    qxy = np.stack([rng.integers(strip.row0 + 2, strip.row1 - 2, nq), rng.integers(0, 512 * MAPSIZE, nq)], 1).astype(np.int32)
+
+    def interactive_step():
+        W.set_rootdensity(rxy, rval)
+        n = one_step().steps
+        W.vertex_fill(vbuf.data_ptr())
+        W.gather_cells(qxy)  # blocks: cells + normals on the host
+        return n
+
+    interactive_step()
+    barrier()
+    t0_i = time.perf_counter()
+    mine_i = 0
+    for _ in range(e2e_steps):
+        mine_i += interactive_step()
+    barrier()
+    dt_i = time.perf_counter() - t0_i
+    tmax_i = torch.tensor([dt_i], dtype=torch.float64, device=dev)
+    tsum_i = torch.tensor([float(mine_i)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax_i, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum_i)
+    del vbuf
+    if rank == 0:
+        line["e2e_device_consumers"] = {
+            "value": float(tsum_i.item()) / float(tmax_i.item()), "unit": UNIT, "ms_per_step": 1e3 * float(tmax_i.item()) / e2e_steps,
+            "h2d_bytes_per_step": int(rxy.nbytes + rval.nbytes + qxy.nbytes), "d2h_bytes_per_step": int(nq * (32 + 12)),
+            "api": "shx_set_rootdensity + shx_erode + shx_vertex_fill (device buffer) + shx_gather_cells (8192 cells and normals to the host)"}
     if rank == 0:
         line["e2e"] = {"value": float(tsum.item()) / float(tmax.item()), "unit": UNIT,
                        "h2d_bytes_per_step": int(rxy.nbytes + rval.nbytes), "d2h_bytes_per_step": int(own_cells * rec_bytes),

@@ -221,6 +221,12 @@ int shx_vertex_fill(shx_ctx* c, float* dev_out);
 int shx_vertex_download(shx_ctx* c, float* host_out, size_t ncells);
 int shx_view_maps(shx_ctx* c, float* dev_out);
 int shx_view_maps_download(shx_ctx* c, float* host_out, size_t ncells);
+/* Sparse read-back for host code that looks at a few cells per frame (Vegetation::grow: discharge /
+ * height / normal / rootdensity at plant positions, vegetation.h:67-85,160-180) instead of the whole
+ * pool: the records of the n queried cells {x, y} and, if normals3 != NULL, World::map.normal there
+ * (cellpool.h:181-204 with the map-level oob of :413-419).  Host buffers; blocks.  A query outside
+ * the map (map.get() == NULL in the reference) or outside a strip's stored rows returns zeros. */
+int shx_gather_cells(shx_ctx* c, const int* xy, size_t n, shx_cell* out, float* normals3);
 
 /* ---- row-strip exchange (multi-GPU): buffers are DEVICE pointers owned by the caller
  * (e.g. torch tensors); the transport between ranks is the caller's (NCCL send/recv or P2P). */

@@ -126,6 +126,7 @@ def lib():
     L.shx_vertex_download.argtypes = [vp, vp, sz]
     L.shx_view_maps.argtypes = [vp, vp]
     L.shx_view_maps_download.argtypes = [vp, vp, sz]
+    L.shx_gather_cells.argtypes = [vp, vp, sz, vp, vp]
     L.shx_strip_message_words.argtypes = [vp, sz]
     L.shx_strip_message_words.restype = sz
     L.shx_strip_pack_message.argtypes = [vp, vp, vp, sz]
@@ -347,6 +348,15 @@ class World:
         out = np.zeros((n, 4), np.float32)
         self._check(self.L.shx_view_maps_download(self._h, out.ctypes.data, n))
         return out
+
+    def gather_cells(self, xy, normals=True):
+        """records (CELL_DTYPE) and World::map.normal of the cells xy[n, 2] (int32)"""
+        xy = np.ascontiguousarray(xy, np.int32)
+        n = xy.shape[0]
+        out = np.zeros(n, CELL_DTYPE)
+        nrm = np.zeros((n, 3), np.float32) if normals else None
+        self._check(self.L.shx_gather_cells(self._h, xy.ctypes.data, n, out.ctypes.data, nrm.ctypes.data if normals else None))
+        return (out, nrm) if normals else out
 
     def strip_message_words(self, cap):
         return int(self.L.shx_strip_message_words(self._h, cap))

@@ -535,6 +535,28 @@ int shx_view_maps_download(shx_ctx* c, float* host_out, size_t ncells) {
   return SHX_OK;
 }
 
+int shx_gather_cells(shx_ctx* c, const int* xy, size_t n, shx_cell* out, float* normals3) {
+  if (!c || (n && (!xy || !out))) return fail(SHX_ERR_ARG, "null argument");
+  if (!n) return SHX_OK;
+  CU(cudaSetDevice(c->cfg.device));
+  // staging: [xy | cells | normals]
+  const size_t b_xy = n * 2 * sizeof(int), b_cells = n * sizeof(shx_cell), b_n = n * 3 * sizeof(float);
+  int rc = view_staging(c, b_xy + b_cells + b_n);
+  if (rc) return rc;
+  char* base = reinterpret_cast<char*>(c->d_view);
+  int* d_xy = reinterpret_cast<int*>(base + b_cells);  // cells first: 32-byte aligned
+  float* d_n = reinterpret_cast<float*>(base + b_cells + b_xy);
+  CU(cudaMemcpyAsync(d_xy, xy, b_xy, cudaMemcpyHostToDevice, c->stream));
+  gather_cells_kernel<<<grid_for(c, n), 256, 0, c->stream>>>(view_args(c), d_xy, n, reinterpret_cast<shx_cell*>(base),
+                                                            normals3 ? d_n : nullptr);
+  c->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, base, b_cells, cudaMemcpyDeviceToHost, c->stream));
+  if (normals3) CU(cudaMemcpyAsync(normals3, d_n, b_n, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return SHX_OK;
+}
+
 // ------------------------------------------------------------------------------- erode pieces
 
 static int fetch_stats(shx_ctx* c, shx_stats* out) {

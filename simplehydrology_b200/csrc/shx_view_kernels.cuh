@@ -89,4 +89,52 @@ __global__ void view_maps_kernel(const ViewArgs a, float4* __restrict__ out, con
   }
 }
 
+// Sparse read-back for host code that only looks at a few cells per frame (Vegetation::grow reads
+// discharge / height / normal / rootdensity at plant positions, vegetation.h:67-85,160-180): the
+// 32-byte records of the queried cells and, optionally, World::map.normal there (cellpool.h:181-204
+// with the MAP-level oob of cellpool.h:413-419, i.e. across tile borders, unlike updatenode).
+// A query outside the map (map.get() == NULL) or outside this strip's stored rows returns zeros.
+__global__ void gather_cells_kernel(const ViewArgs a, const int* __restrict__ xy, const size_t n, shx_cell* __restrict__ out,
+                                    float* __restrict__ normals) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = xy[2 * i], y = xy[2 * i + 1];
+    const int size = a.m.size;
+    float4 lo = make_float4(0.0f, 0.0f, 0.0f, 0.0f), hi = lo;
+    float nx = 0.0f, ny = 0.0f, nz = 0.0f;
+    // the normal needs rows x-1 .. x+1: all stored, or outside the map
+    const bool have = x >= 0 && x < size && y >= 0 && y < size && x >= a.m.xlo && x < a.m.xlo + a.m.nrows &&
+                      (x - 1 >= a.m.xlo || x == 0) && (x + 1 < a.m.xlo + a.m.nrows || x == size - 1);
+    if (have) {
+      const size_t c = (size_t)(x - a.m.xlo) * size + y;
+      const float4 f = __ldg(reinterpret_cast<const float4*>(a.m.rec + c));
+      const int4 t = __ldg(reinterpret_cast<const int4*>(a.m.rec + c) + 1);
+      const float hc = view_height(a, x, y);
+      if (a.sequential) {
+        lo = make_float4(hc, f.x, f.y, f.z);
+        hi = make_float4(__int_as_float(t.x), __int_as_float(t.y), __int_as_float(t.z), f.w);
+      } else {
+        lo = make_float4(hc, f.x, f.y, f.z);
+        hi = make_float4(t_to_float(t.x), t_to_float(t.y), t_to_float(t.z), f.w);
+      }
+      const bool xm = x > 0, xp = x < size - 1, ym = y > 0, yp = y < size - 1;
+      const float hxp = xp ? view_height(a, x + 1, y) : 0.0f, hxm = xm ? view_height(a, x - 1, y) : 0.0f;
+      const float hyp = yp ? view_height(a, x, y + 1) : 0.0f, hym = ym ? view_height(a, x, y - 1) : 0.0f;
+      const float Bp = a.mapscale * (hxp - hc), Bm = a.mapscale * (hxm - hc);
+      const float Ap = a.mapscale * (hyp - hc), Am = a.mapscale * (hym - hc);
+      if (xp && yp) { nx += -Bp; ny += 1.0f; nz += -Ap; }
+      if (xm && ym) { nx += Bm; ny += 1.0f; nz += Am; }
+      if (xp && ym) { nx += -Bp; ny += 1.0f; nz += Am; }
+      if (xm && yp) { nx += Bm; ny += 1.0f; nz += -Ap; }
+      const float l2 = nx * nx + ny * ny + nz * nz;
+      if (l2 > 0.0f) {
+        const float inv = 1.0f / sqrtf(l2);
+        nx *= inv; ny *= inv; nz *= inv;
+      }
+    }
+    reinterpret_cast<float4*>(out + i)[0] = lo;
+    reinterpret_cast<float4*>(out + i)[1] = hi;
+    if (normals) { normals[3 * i] = nx; normals[3 * i + 1] = ny; normals[3 * i + 2] = nz; }
+  }
+}
+
 }  // namespace shx

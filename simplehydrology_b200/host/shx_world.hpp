@@ -102,6 +102,11 @@ class Bridge {
   // map order {erf(0.4*discharge), 0.5*(1+erf(momentumx)), 0.5*(1+erf(momentumy)), height}
   void view_maps(float* rgba) { check(shx_view_maps_download(ctx_, rgba, ncells_), "shx_view_maps_download"); }
 
+  // sparse read-back instead of the pool download: the records (and World::map.normal) of n cells {x, y}
+  void gather(const int* xy, size_t n, shx_cell* out, float* normals3 = nullptr) {
+    check(shx_gather_cells(ctx_, xy, n, out, normals3), "shx_gather_cells");
+  }
+
   shx_ctx* context() { return ctx_; }
   const shx_params& params() const { return params_; }
 

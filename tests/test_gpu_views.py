@@ -70,3 +70,34 @@ def test_vertex_fill_into_a_caller_owned_device_buffer_and_strips():
             S.synth_terrain(5)
             parts.append(S.vertex_download())
     assert np.array_equal(np.concatenate(parts), whole)
+
+
+def test_gather_cells_returns_records_and_map_normals(golden, init_cells):
+    """shx_gather_cells: the sparse read-back for Vegetation::grow-style host code"""
+    cells_xy = [(0, 0), (0, 5), (511, 511), (511, 0), (3, 511), (200, 200), (17, 340), (0, 511)]  # tests/golden NORMAL_CELLS
+    with shx.World(mapsize=1, mode=shx.MODE_SEQUENTIAL) as W:
+        W.upload(init_cells)
+        rec, nrm = W.gather_cells(cells_xy)
+        assert np.array_equal(bits(nrm + np.float32(0.0)), bits(golden["normals"] + np.float32(0.0)))  # World::map.normal of the reference
+        idx = orc.tiled_index_map(orc.default_params(1))
+        want = init_cells[[idx[x, y] for x, y in cells_xy]]
+        assert np.array_equal(rec.view(np.uint8), want.view(np.uint8))
+        # outside the map: map.get() == NULL in the reference -> zeros here
+        rec, nrm = W.gather_cells([(-1, 3), (512, 0), (5, 512), (5, -1)])
+        assert not rec.view(np.uint8).any() and not nrm.any()
+        assert W.gather_cells(np.zeros((0, 2), np.int32), normals=False).size == 0
+    # batched mode on a tiled world after erosion: every field equals the full download; normals cross tile borders
+    ms = 2
+    p = orc.default_params(ms)
+    with shx.World(mapsize=ms) as W:
+        W.synth_terrain(4)
+        W.erode(256, 3)
+        full = W.download()
+        rng = np.random.default_rng(2)
+        xy = np.concatenate([rng.integers(0, 1024, size=(500, 2)), [[511, 300], [512, 300], [300, 511], [300, 512], [0, 0], [1023, 1023]]])
+        rec, nrm = W.gather_cells(xy)
+    idx = orc.tiled_index_map(p)
+    assert np.array_equal(rec.view(np.uint8), full[idx[xy[:, 0], xy[:, 1]]].view(np.uint8))
+    S = orc.Seq(full.copy(), params=p)
+    want = np.stack([S.normal(int(x), int(y)) for x, y in xy])
+    assert np.array_equal(nrm + np.float32(0.0), want + np.float32(0.0))
