@@ -13,7 +13,7 @@
 //
 // Per call it (1) copies the current Drop::/World:: statics, (2) pushes the rootdensity cells the
 // host changed since the last call (vegetation.h:87-118 writes them in place), (3) runs the batched
-// CUDA erode and (4) brings height / discharge / momentum back into the same pool records, so the
+// CUDA erode and (4) brings the cell records back into the same pool, so the
 // renderer, the texture builders (SimpleHydrology.cpp:341-354) and vegetation.h read the result
 // unchanged.  Errors: the reference reports none; the bridge throws std::runtime_error for misuse
 // of the boundary or CUDA failures (there is no CPU fallback to degrade to).
@@ -80,7 +80,10 @@ class Bridge {
     push_rootdensity();
     shx_stats st;
     check(shx_erode(ctx_, cycles, seed, &st), "shx_erode");
-    check(shx_download(ctx_, pool_, ncells_, SHX_F_HEIGHT | SHX_F_DISCHARGE | SHX_F_MOMENTUM), "shx_download");
+    // Whole records: one contiguous DMA per tile.  (Selecting height/discharge/momentum only makes it a
+    // strided 16-of-32-byte copy, measured 2x SLOWER at 8192^2.)  rootdensity comes back as pushed above;
+    // the *_track fields are scratch of the erode call (world.h:56-61 zeroes them first thing).
+    check(shx_download(ctx_, pool_, ncells_, SHX_F_ALL), "shx_download");
     return st;
   }
 

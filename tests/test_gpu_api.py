@@ -170,6 +170,6 @@ def test_cpp_host_adaptor_equals_the_python_path(tmp_path, init_cells):
                     val.append(host["rootdensity"][i])
             W.set_rootdensity(np.array(xy, np.int32), np.array(val, np.float32))
             W.erode(cycles, seed=1)
-            W.download(out=host, mask=shx.F_HEIGHT | shx.F_DISCHARGE | shx.F_MOMENTUM)
+            W.download(out=host, mask=shx.F_ALL)
     assert np.array_equal(got.view(np.uint8), host.view(np.uint8))
     assert "total steps" in r.stdout
