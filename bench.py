@@ -221,6 +221,13 @@ def run_cuda(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot)
+    # per-rank view of the same K steps: strips are static, drops concentrate in valleys (report imbalance)
+    per_rank = torch.tensor([ms, tm.descend_ms, float(acc["steps"])], dtype=torch.float64, device=dev)
+    ranks = [torch.zeros_like(per_rank) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(ranks, per_rank)
+    else:
+        ranks = [per_rank]
     ms = float(t.item())
     total = dict(zip(names, [int(v) for v in tot.tolist()]))
     psteps = total["steps"]
@@ -264,6 +271,9 @@ def run_cuda(args):
         if world > 1:
             if not peer:
                 line["exchange_rounds_per_cycle"] = rounds / max(args.steps, 1)
+            k = max(args.steps, 1)
+            line["per_rank"] = {"ms_per_step": [float(r[0]) / k for r in ranks], "kernel_ms_per_cycle": [float(r[1]) / k for r in ranks],
+                                "particle_steps_per_cycle": [float(r[2]) / k for r in ranks]}
 
     # ---- the per-frame consumers that follow erode in the reference's loop, as device
     # kernels on the resident world: vertex fill (updatenode) and the discharge / momentum maps
