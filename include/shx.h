@@ -126,6 +126,12 @@ typedef struct {
    * Every rank must make the same sequence of erode / run calls.  size/world must be a power of two
    * and a multiple of tilesize. */
   int peer_rank, peer_world;
+  /* batched mode: at most this many drops per node march together; a call with more cycles runs as
+   * consecutive batches (reset once before, EMA once after).  All drops of a batch read the same
+   * frozen heights each step, so the batch must stay sparse: 512 per 512^2 node per batch is what
+   * the reference's frame loop issues (SimpleHydrology.cpp:319); much denser batches over-erode
+   * cells several drops share and can run away.  0 = 512. */
+  int max_cycles_per_launch;
 } shx_config;
 
 /* CUDA IPC handles of one rank's strip (opaque bytes; gather them from all ranks with the caller's

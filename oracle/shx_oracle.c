@@ -496,7 +496,19 @@ static uint32_t ls_cascade_block(const orc_params* P, int32_t* B, const int* inb
 /* One phase of one drop: [cascade owed from the previous step] + one Drop::descend
  * (water.h:58-156) reading plane R only; all height changes go to the 3x3 delta block
  * D around (ix,iy).  Returns 1 if the drop was processed (D/ix/iy valid). */
-static int ls_step(orc_ls_world* w, const int32_t* R, orc_drop* d, int32_t* D, int* pix, int* piy, orc_stats* st) {
+/* what the drop itself added to cell (x, y) in the earlier steps of the current phase (S > 1) */
+typedef struct { const int32_t* D; const int* pos; int n; } ls_own;
+static int32_t ls_own_delta(const ls_own* own, int x, int y) {
+  int32_t v = 0;
+  if (!own) return 0;
+  for (int s = 0; s < own->n; s++) {
+    const int ox = x - own->pos[2 * s], oy = y - own->pos[2 * s + 1];
+    if (ox >= -1 && ox <= 1 && oy >= -1 && oy <= 1) v += own->D[9 * s + (ox + 1) * 3 + (oy + 1)];
+  }
+  return v;
+}
+
+static int ls_step(orc_ls_world* w, const int32_t* R, orc_drop* d, int32_t* D, int* pix, int* piy, orc_stats* st, const ls_own* own) {
   const orc_params* P = &w->p;
   const int size = w->size;
   const float lod = (float)P->lodsize;
@@ -508,7 +520,7 @@ static int ls_step(orc_ls_world* w, const int32_t* R, orc_drop* d, int32_t* D, i
     for (int dy = -1; dy <= 1; dy++) {
       const int k = (dx + 1) * 3 + (dy + 1);
       inb[k] = !ls_oob(w, ix + dx, iy + dy);
-      B[k] = inb[k] ? R[(size_t)(ix + dx) * size + (iy + dy)] : 0;
+      B[k] = inb[k] ? R[(size_t)(ix + dx) * size + (iy + dy)] + ls_own_delta(own, ix + dx, iy + dy) : 0;
       D[k] = 0;
     }
   st->steps++;
@@ -582,7 +594,7 @@ static int ls_step(orc_ls_world* w, const int32_t* R, orc_drop* d, int32_t* D, i
   else {
     const int ddx = nix - ix, ddy = niy - iy;
     if (ddx >= -1 && ddx <= 1 && ddy >= -1 && ddy <= 1) h2 = hf(B[(ddx + 1) * 3 + (ddy + 1)]);
-    else h2 = hf(R[(size_t)nix * size + niy]); /* :124 */
+    else h2 = hf(R[(size_t)nix * size + niy] + ls_own_delta(own, nix, niy)); /* :124 */
   }
   float c_eq = (1.0f + P->entrainment * orc_erff_poly(0.4f * discharge)) * (hc - h2); /* :127-128 */
   if (c_eq < 0) c_eq = 0;
@@ -614,9 +626,10 @@ static int ls_step(orc_ls_world* w, const int32_t* R, orc_drop* d, int32_t* D, i
 
 void orc_ls_run(orc_ls_world* w, orc_drop* drops, size_t n, orc_stats* st, float* trace0, int trace_cap, int* trace_n) {
   const int size = w->size;
-  int32_t* deltas = (int32_t*)calloc(n * 9, sizeof(int32_t)); /* this phase */
-  int* dpos = (int*)calloc(n * 2, sizeof(int));
-  unsigned char* has = (unsigned char*)calloc(n, 1);
+  const int S = w->steps_per_phase > 1 ? w->steps_per_phase : 1;
+  int32_t* deltas = (int32_t*)calloc(n * 9 * S, sizeof(int32_t)); /* this phase: S blocks per drop */
+  int* dpos = (int*)calloc(n * 2 * S, sizeof(int));
+  unsigned char* has = (unsigned char*)calloc(n * S, 1);
   int tn = 0;
   orc_stats local;
   memset(&local, 0, sizeof(local));
@@ -624,25 +637,29 @@ void orc_ls_run(orc_ls_world* w, orc_drop* drops, size_t n, orc_stats* st, float
     const int32_t* R = w->h[phase & 1];
     size_t active = 0;
     for (size_t i = 0; i < n; i++) {
-      has[i] = 0;
+      int done = 0; /* steps this drop made in this phase */
+      for (int s = 0; s < S; s++) has[i * S + s] = 0;
       if (!(drops[i].flags & ORC_DROP_ALIVE)) continue;
-      if (w->align_age && (uint64_t)drops[i].age > phase) { /* still asleep: counts as active, does nothing */
-        active++;
-        continue;
-      }
-      has[i] = (unsigned char)ls_step(w, R, &drops[i], deltas + 9 * i, &dpos[2 * i], &dpos[2 * i + 1], &local);
-      if (drops[i].flags & (ORC_DROP_DONE_AGE | ORC_DROP_DONE_VOL | ORC_DROP_DONE_OOB)) drops[i].flags &= ~ORC_DROP_ALIVE;
       active++;
-      if (i == 0 && trace0 && tn < trace_cap) {
-        float* t = trace0 + 7 * (size_t)tn++;
-        t[0] = (float)drops[0].age; t[1] = drops[0].px; t[2] = drops[0].py; t[3] = drops[0].sx; t[4] = drops[0].sy;
-        t[5] = drops[0].volume; t[6] = drops[0].sediment;
+      for (int s = 0; s < S; s++) {
+        if (!(drops[i].flags & ORC_DROP_ALIVE)) break;
+        if (w->align_age && (uint64_t)drops[i].age > phase * S + s) continue; /* still asleep: counts as active, does nothing */
+        const ls_own own = {deltas + 9 * (i * S), dpos + 2 * (i * S), done};
+        has[i * S + done] = (unsigned char)ls_step(w, R, &drops[i], deltas + 9 * (i * S + done), &dpos[2 * (i * S + done)],
+                                                   &dpos[2 * (i * S + done) + 1], &local, done ? &own : NULL);
+        done++;
+        if (drops[i].flags & (ORC_DROP_DONE_AGE | ORC_DROP_DONE_VOL | ORC_DROP_DONE_OOB)) drops[i].flags &= ~ORC_DROP_ALIVE;
+        if (i == 0 && trace0 && tn < trace_cap) {
+          float* t = trace0 + 7 * (size_t)tn++;
+          t[0] = (float)drops[0].age; t[1] = drops[0].px; t[2] = drops[0].py; t[3] = drops[0].sx; t[4] = drops[0].sy;
+          t[5] = drops[0].volume; t[6] = drops[0].sediment;
+        }
       }
     }
     if (active == 0) break;
     /* The kernel adds every delta to BOTH planes (the one not being read now, and the
      * other one a phase later); sequentially that is just: apply to both. */
-    for (size_t i = 0; i < n; i++) {
+    for (size_t i = 0; i < n * S; i++) {
       if (!has[i]) continue;
       for (int k = 0; k < 9; k++) {
         const int32_t v = deltas[9 * i + k];
@@ -694,12 +711,27 @@ void orc_ls_erode_spawnlist(orc_ls_world* w, const float* xy, size_t n, orc_stat
   free(drops);
 }
 
+/* World::erode (world.h:54-88) with hash spawns.  At most max_cycles_per_launch (0 = 512) drops per
+ * node march together; more cycles run as consecutive batches between ONE reset and ONE EMA
+ * (shx_config.max_cycles_per_launch). */
 void orc_ls_erode(orc_ls_world* w, int cycles, uint64_t seed, uint64_t epoch, orc_stats* st) {
-  const size_t n = (size_t)w->p.mapsize * w->p.mapsize * (size_t)cycles;
+  const int nodes = w->p.mapsize * w->p.mapsize;
+  const int cap = w->max_cycles_per_launch > 0 ? w->max_cycles_per_launch : 512;
+  const size_t n = (size_t)nodes * (size_t)cycles;
   float* xy = (float*)malloc(sizeof(float) * 2 * (n ? n : 1));
-  orc_ls_spawn(&w->p, seed, epoch, cycles, xy);
-  orc_ls_erode_spawnlist(w, xy, n, st);
-  free(xy);
+  float* sub = (float*)malloc(sizeof(float) * 2 * ((size_t)nodes * cap));
+  orc_drop* drops = (orc_drop*)malloc(sizeof(orc_drop) * ((size_t)nodes * cap));
+  orc_ls_spawn(&w->p, seed, epoch, cycles, xy); /* node-major: drop i of node at node*cycles + i */
+  orc_ls_reset_tracks(w);
+  for (int i0 = 0; i0 < cycles; i0 += cap) {
+    const int m = cycles - i0 < cap ? cycles - i0 : cap;
+    for (int node = 0; node < nodes; node++)
+      memcpy(sub + 2 * ((size_t)node * m), xy + 2 * ((size_t)node * cycles + i0), sizeof(float) * 2 * m);
+    orc_ls_make_drops(w, sub, (size_t)nodes * m, drops, st); /* the 0.1 rejection sees the heights the earlier batches left */
+    orc_ls_run(w, drops, (size_t)nodes * m, st, NULL, 0, NULL);
+  }
+  orc_ls_ema(w, 1);
+  free(xy); free(sub); free(drops);
 }
 
 /* ================================================================== synthetic terrain */

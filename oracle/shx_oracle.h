@@ -123,6 +123,9 @@ typedef struct {
   orc_track* track; /* Q13.18 accumulators */
   int row0, row1;   /* rows [row0,row1) are owned (strip); 0,size for the whole map */
   int align_age;    /* != 0: a drop of age a sleeps until phase a (drops carried over from the previous call) */
+  int max_cycles_per_launch; /* orc_ls_erode: drops per node that march together (0 = 512), shx_config's field */
+  int steps_per_phase; /* S >= 1 steps between two global meetings; within a phase a drop reads the frozen
+                          plane plus its OWN earlier deltas of the phase (0 is read as 1) */
 } orc_ls_world;
 
 orc_ls_world* orc_ls_create(const orc_params* p);

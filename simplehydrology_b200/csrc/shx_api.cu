@@ -707,7 +707,9 @@ static int run_device_drops(shx_ctx* c, size_t n, bool trace, bool align_age = f
   return SHX_OK;
 }
 
-static int spawn_device(shx_ctx* c, int cycles, uint64_t seed, uint64_t epoch, size_t* n_out) {
+static int batch_cycles(const shx_ctx* c) { return c->cfg.max_cycles_per_launch > 0 ? c->cfg.max_cycles_per_launch : 512; }
+
+static int spawn_device(shx_ctx* c, int cycles, uint64_t seed, uint64_t epoch, size_t* n_out, int i0 = 0) {
   const int ts = c->p.tilesize, ms = c->p.mapsize;
   if (cycles < 0) return fail(SHX_ERR_ARG, "negative cycles");
   if (c->m.row0 % ts || c->m.row1 % ts) return fail(SHX_ERR_ARG, "spawning needs tile-aligned strips");
@@ -720,7 +722,7 @@ static int spawn_device(shx_ctx* c, int cycles, uint64_t seed, uint64_t epoch, s
   a.m = c->m;
   a.sequential = sequential(c) ? 1 : 0;
   a.tilesize = ts; a.mapsize = ms;
-  a.node0 = node0; a.nnodes = nnodes; a.cycles = cycles;
+  a.node0 = node0; a.nnodes = nnodes; a.cycles = cycles; a.i0 = i0;
   a.key = mix64(mix64(seed) + epoch);
   a.drops = c->d_drops;
   a.xy = c->d_xy;
@@ -776,14 +778,20 @@ int shx_erode_async(shx_ctx* c, int cycles, uint64_t seed) {
   int rc = begin_call(c);
   if (rc) return rc;
   if (!c->tracks_clean && (rc = shx_reset_tracks(c))) return rc;  // world.h:56-61
-  size_t n = 0;
-  if ((rc = span_begin(c, 0))) return rc;
-  if ((rc = spawn_device(c, cycles, seed, c->epoch, &n))) return rc;  // world.h:64-74
-  if ((rc = span_end(c))) return rc;
+  // world.h:64-76 in batches of at most max_cycles_per_launch drops per node (sequential mode marches
+  // the drops one by one anyway).  A peer-mode rank always launches once, even with nothing to spawn.
+  const int cap = sequential(c) ? std::max(cycles, 1) : batch_cycles(c);
+  for (int i0 = 0; i0 < cycles || i0 == 0; i0 += cap) {
+    const int sub = std::max(0, std::min(cap, cycles - i0));
+    size_t n = 0;
+    if ((rc = span_begin(c, 0))) return rc;
+    if ((rc = spawn_device(c, sub, seed, c->epoch, &n, i0))) return rc;
+    if ((rc = span_end(c))) return rc;
+    if ((rc = span_begin(c, 1))) return rc;
+    if ((rc = run_device_drops(c, n, false))) return rc;
+    if ((rc = span_end(c))) return rc;
+  }
   c->epoch++;
-  if ((rc = span_begin(c, 1))) return rc;
-  if ((rc = run_device_drops(c, n, false))) return rc;  // world.h:76
-  if ((rc = span_end(c))) return rc;
   if ((rc = span_begin(c, 2))) return rc;
   if ((rc = ema_launch(c, !c->cfg.keep_tracks))) return rc;  // world.h:81-86
   return span_end(c);
@@ -1067,6 +1075,7 @@ int shx_strip_run_device_drops(shx_ctx* c, const shx_drop* dev_drops, size_t n, 
 int shx_strip_erode_begin_with(shx_ctx* c, int cycles, uint64_t seed, const shx_drop* dev_carried, size_t n_carried) {
   if (!c) return fail(SHX_ERR_ARG, "null context");
   if (n_carried && !dev_carried) return fail(SHX_ERR_ARG, "null carried drops");
+  if (cycles > batch_cycles(c)) return fail(SHX_ERR_ARG, "a strip call takes at most max_cycles_per_launch cycles (migrants are packed once per call)");
   int rc = begin_call(c);
   if (rc) return rc;
   c->strip_open = true;

@@ -13,7 +13,8 @@ struct SpawnArgs {
   int sequential;
   int tilesize, mapsize;
   unsigned node0, nnodes;
-  int cycles;
+  int cycles;      // drops per node in this batch
+  int i0;          // index of the batch's first drop within the node's drops of the call
   uint64_t key;
   shx_drop* drops;
   float* xy;  // optional copy of the positions
@@ -45,7 +46,7 @@ __device__ __forceinline__ shx_drop make_drop(float x, float y, const MapView& m
 __global__ void spawn_kernel(const SpawnArgs a) {
   const unsigned n = a.nnodes * (unsigned)a.cycles;
   for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    const unsigned node = a.node0 + k / (unsigned)a.cycles, i = k % (unsigned)a.cycles;
+    const unsigned node = a.node0 + k / (unsigned)a.cycles, i = (unsigned)a.i0 + k % (unsigned)a.cycles;
     const uint64_t r = mix64(a.key + (((uint64_t)node << 32) | (uint64_t)i));
     const int nx = (int)(node / (unsigned)a.mapsize) * a.tilesize, ny = (int)(node % (unsigned)a.mapsize) * a.tilesize;
     const float x = (float)(nx + (int)((uint32_t)r % (uint32_t)a.tilesize));

@@ -107,6 +107,22 @@ def test_hash_spawned_erode_matches_oracle(init_cells):
     W.close()
 
 
+@pytest.mark.parametrize("cap", [0, 300, 1536])
+def test_large_calls_run_as_batches(init_cells, cap):
+    """erode(cycles) with more cycles than shx_config.max_cycles_per_launch (0 = 512): consecutive lock-step
+    batches between one reset and one EMA, batch k holding drops [k*cap, (k+1)*cap) of every node"""
+    W, ls = make_world(init_cells, orc.default_params(1), max_cycles_per_launch=cap)
+    ls.w.contents.max_cycles_per_launch = cap
+    for epoch in range(2):
+        st = W.erode(1536, seed=5)
+        so = ls.erode(1536, 5, epoch)
+        assert_stats_equal(st, so)
+    assert_state_equal(W, ls, f"batched call, cap {cap}")
+    batches = -(-1536 // (cap or 512))
+    assert st.launches == 2 * batches + 1  # (spawn + descend) per batch, one fused EMA/reset
+    W.close()
+
+
 @pytest.mark.parametrize("tilesize,mapsize,n", [(64, 1, 40), (64, 3, 700), (32, 4, 2000), (128, 2, 1500)])
 def test_reduced_geometries_and_tiling(tilesize, mapsize, n):
     p, cells = small_world(tilesize, mapsize, seed=tilesize + mapsize)
