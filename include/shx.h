@@ -77,7 +77,8 @@ enum {
   SHX_DROP_REJECTED = 32,    /* world.h:71-72 */
   SHX_DROP_DONE_NULL = 64,   /* water.h:62-68 */
   SHX_DROP_MIGRATE_LO = 128, /* left this strip towards smaller x */
-  SHX_DROP_MIGRATE_HI = 256
+  SHX_DROP_MIGRATE_HI = 256,
+  SHX_DROP_WAITED_SHIFT = 16 /* bits 16-18: phases the drop has been waiting for its cell (batched mode, saturating at 7) */
 };
 
 /* Counters of one call.  fx_* are exact integers: heights in Q5.26 (2^-26 units),

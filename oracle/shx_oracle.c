@@ -377,6 +377,7 @@ orc_ls_world* orc_ls_create(const orc_params* p) {
   w->track = (orc_track*)calloc(n, sizeof(orc_track));
   w->row0 = 0;
   w->row1 = w->size;
+  w->exclusive_cells = 1;
   return w;
 }
 
@@ -496,6 +497,21 @@ static uint32_t ls_cascade_block(const orc_params* P, int32_t* B, const int* inb
 /* One phase of one drop: [cascade owed from the previous step] + one Drop::descend
  * (water.h:58-156) reading plane R only; all height changes go to the 3x3 delta block
  * D around (ix,iy).  Returns 1 if the drop was processed (D/ix/iy valid). */
+/* Same-cell exclusion of the lock step: of the drops that stand on one cell in a phase only the holder of the
+ * highest key steps, the others wait a phase (a drop reads frozen heights, so two drops eroding one cell in the
+ * same phase would both take the full amount: over-erosion that feeds on itself in busy river cells).
+ * key = {phase tag | phases waited so far, saturating at 7 : 3 | hash of the drop's state : 13}: longest waiting
+ * first, then an order-independent pseudo-random choice; drops with equal keys all step. */
+static uint32_t ls_claim_key(uint32_t tag, const orc_drop* d) {
+  uint32_t px, py;
+  memcpy(&px, &d->px, 4);
+  memcpy(&py, &d->py, 4);
+  uint32_t h = px * 0x9E3779B1u ^ py * 0x85EBCA77u ^ (uint32_t)d->age * 0xC2B2AE3Du;
+  h ^= h >> 15;
+  const uint32_t waited = ((uint32_t)d->flags >> ORC_DROP_WAITED_SHIFT) & 7u;
+  return (tag << 16) | (waited << 13) | (h & 0x1FFFu);
+}
+
 /* what the drop itself added to cell (x, y) in the earlier steps of the current phase (S > 1) */
 typedef struct { const int32_t* D; const int* pos; int n; } ls_own;
 static int32_t ls_own_delta(const ls_own* own, int x, int y) {
@@ -633,14 +649,33 @@ void orc_ls_run(orc_ls_world* w, orc_drop* drops, size_t n, orc_stats* st, float
   int tn = 0;
   orc_stats local;
   memset(&local, 0, sizeof(local));
+  /* exclusive_cells: claim[c] = highest key {phase tag, phases waited, state hash} of the awake drops on cell c */
+  uint32_t* claim = w->exclusive_cells ? (uint32_t*)calloc((size_t)size * size, sizeof(uint32_t)) : NULL;
   for (uint64_t phase = 0;; phase++) {
     const int32_t* R = w->h[phase & 1];
     size_t active = 0;
+    if (claim)
+      for (size_t i = 0; i < n; i++) {
+        if (!(drops[i].flags & ORC_DROP_ALIVE)) continue;
+        if (w->align_age && (uint64_t)drops[i].age > phase * S) continue;
+        const size_t c = (size_t)trunc_i(drops[i].px) * size + trunc_i(drops[i].py);
+        const uint32_t key = ls_claim_key((uint32_t)phase + 1u, &drops[i]);
+        if (claim[c] < key) claim[c] = key;
+      }
     for (size_t i = 0; i < n; i++) {
       int done = 0; /* steps this drop made in this phase */
       for (int s = 0; s < S; s++) has[i * S + s] = 0;
       if (!(drops[i].flags & ORC_DROP_ALIVE)) continue;
       active++;
+      if (claim && !(w->align_age && (uint64_t)drops[i].age > phase * S)) {
+        const size_t c = (size_t)trunc_i(drops[i].px) * size + trunc_i(drops[i].py);
+        if (claim[c] != ls_claim_key((uint32_t)phase + 1u, &drops[i])) { /* another drop has the cell this phase */
+          const int waited = (drops[i].flags >> ORC_DROP_WAITED_SHIFT) & 7;
+          drops[i].flags = (drops[i].flags & ~(7 << ORC_DROP_WAITED_SHIFT)) | ((waited < 7 ? waited + 1 : 7) << ORC_DROP_WAITED_SHIFT);
+          continue;
+        }
+        drops[i].flags &= ~(7 << ORC_DROP_WAITED_SHIFT);
+      }
       for (int s = 0; s < S; s++) {
         if (!(drops[i].flags & ORC_DROP_ALIVE)) break;
         if (w->align_age && (uint64_t)drops[i].age > phase * S + s) continue; /* still asleep: counts as active, does nothing */
@@ -678,7 +713,7 @@ void orc_ls_run(orc_ls_world* w, orc_drop* drops, size_t n, orc_stats* st, float
     st->fx_eroded += local.fx_eroded; st->fx_deposited += local.fx_deposited;
     st->fx_sed_oob_lost += local.fx_sed_oob_lost; st->fx_sed_deposited += local.fx_sed_deposited; st->fx_sed_inflation += local.fx_sed_inflation;
   }
-  free(deltas); free(dpos); free(has);
+  free(deltas); free(dpos); free(has); free(claim);
 }
 
 void orc_ls_reset_tracks(orc_ls_world* w) { /* world.h:56-61 */

@@ -65,7 +65,8 @@ enum {
   ORC_DROP_REJECTED = 32,    /* world.h:71-72 */
   ORC_DROP_DONE_NULL = 64,   /* water.h:62-68 (spawned outside the map) */
   ORC_DROP_MIGRATE_LO = 128, /* left the strip towards smaller x (multi-GPU hand-off) */
-  ORC_DROP_MIGRATE_HI = 256
+  ORC_DROP_MIGRATE_HI = 256,
+  ORC_DROP_WAITED_SHIFT = 16 /* bits 16-18: phases the drop has waited for its cell (lock-step exclusion), saturating at 7 */
 };
 
 typedef struct {
@@ -124,6 +125,8 @@ typedef struct {
   int row0, row1;   /* rows [row0,row1) are owned (strip); 0,size for the whole map */
   int align_age;    /* != 0: a drop of age a sleeps until phase a (drops carried over from the previous call) */
   int max_cycles_per_launch; /* orc_ls_erode: drops per node that march together (0 = 512), shx_config's field */
+  int exclusive_cells; /* != 0 (default): of the drops that stand on the same cell in a phase only the holder of
+                          the highest claim key steps; the others wait for the next phase */
   int steps_per_phase; /* S >= 1 steps between two global meetings; within a phase a drop reads the frozen
                           plane plus its OWN earlier deltas of the phase (0 is read as 1) */
 } orc_ls_world;

@@ -77,6 +77,7 @@ struct shx_ctx {
   PeerView pv{};
   unsigned long long* d_inbox = nullptr;
   unsigned peer_seq = 0;
+  unsigned claim_epoch = 0;  // launch counter mod 15 (+1), see next_claim_epoch
   void* peer_opened[3 * kMaxPeers] = {};
   bool timing = false;
   std::vector<TimingSpan> spans;
@@ -232,7 +233,7 @@ int shx_create(shx_ctx** out, const shx_params* p, const shx_config* cfg_in) {
       return fail(SHX_ERR_NOMEM, "cudaMalloc failed for " #ptr);           \
     }                                                                      \
   } while (0)
-  ALLOC(c->m.hq, c->stored_cells * sizeof(int2));
+  ALLOC(c->m.hq, c->stored_cells * sizeof(int4));
   ALLOC(c->m.rec, c->stored_cells * sizeof(CellRec));
   ALLOC(c->d_drops, c->max_drops * sizeof(shx_drop));
   ALLOC(c->d_xy, c->max_drops * 2 * sizeof(float));
@@ -252,7 +253,7 @@ int shx_create(shx_ctx** out, const shx_params* p, const shx_config* cfg_in) {
     shx_destroy(c);
     return fail(SHX_ERR_NOMEM, "cudaMallocHost failed");
   }
-  cudaMemset(c->m.hq, 0, c->stored_cells * sizeof(int2));
+  cudaMemset(c->m.hq, 0, c->stored_cells * sizeof(int4));
   cudaMemset(c->m.rec, 0, c->stored_cells * sizeof(CellRec));
   cudaMemset(c->d_stats, 0, ST_COUNT * 8);
   cudaMemset(c->d_flags, 0, 4 * sizeof(int));
@@ -456,11 +457,21 @@ int shx_download(shx_ctx* c, shx_cell* pool, size_t ncells, unsigned mask) {
   return SHX_OK;
 }
 
+static int view_staging(shx_ctx* c, size_t bytes);
+
 int shx_download_raw(shx_ctx* c, int32_t* hq2, void* rec32) {
   if (!c) return fail(SHX_ERR_ARG, "null context");
   CU(cudaSetDevice(c->cfg.device));
   CU(cudaStreamSynchronize(c->stream));
-  if (hq2) CU(cudaMemcpy(hq2, c->m.hq, c->stored_cells * sizeof(int2), cudaMemcpyDeviceToHost));
+  if (hq2) {  // the two height words of every stored cell (the claim words stay behind)
+    int rc = view_staging(c, c->stored_cells * sizeof(int2));
+    if (rc) return rc;
+    const int grid = (int)std::min<size_t>((c->stored_cells + 255) / 256, (size_t)c->sm_count * 16);
+    copy_heights_kernel<<<grid, 256, 0, c->stream>>>(c->m.hq, reinterpret_cast<int2*>(c->d_view), c->stored_cells);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(hq2, c->d_view, c->stored_cells * sizeof(int2), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
   if (rec32) CU(cudaMemcpy(rec32, c->m.rec, c->stored_cells * sizeof(CellRec), cudaMemcpyDeviceToHost));
   return SHX_OK;
 }
@@ -568,8 +579,10 @@ static int fetch_stats(shx_ctx* c, shx_stats* out) {
     memcpy(out, c->h_stats, sizeof(shx_stats));
     out->launches = c->launches;
   }
-  if (c->peer && c->h_flags[2]) {
+  if (c->h_flags[2]) {
+    const int why = c->h_flags[2];
     CU(cudaMemsetAsync(c->d_flags + 2, 0, sizeof(int), c->stream));
+    if (why == 2) return fail(SHX_ERR_RANGE, "a launch needed more than 16000 phases (drops queueing for one cell); the call's result is invalid");
     return fail(SHX_ERR_PEER, "a peer GPU did not reach a phase barrier within the time-out; the call's result is invalid");
   }
   if (c->h_flags[0]) {
@@ -614,6 +627,20 @@ int shx_ema(shx_ctx* c) {
   return ema_launch(c, false);
 }
 
+// Claim keys carry a 4-bit launch epoch so that the keys earlier launches left in the cells lose
+// against this launch's; when it wraps, the claim words are cleared (one pass over the height plane
+// every 15 launches).  Peer mode: every rank counts the same launches, so the epochs agree.
+static int next_claim_epoch(shx_ctx* c) {
+  if (++c->claim_epoch > 15u) {
+    const int grid = (int)std::min<size_t>((c->stored_cells + 255) / 256, (size_t)c->sm_count * 16);
+    clear_claims_kernel<<<grid, 256, 0, c->stream>>>(c->m.hq, c->stored_cells);
+    c->launches++;
+    CU(cudaGetLastError());
+    c->claim_epoch = 1u;
+  }
+  return SHX_OK;
+}
+
 // march n drops already in c->d_drops
 static int run_device_drops(shx_ctx* c, size_t n, bool trace, bool align_age = false) {
   c->last_n = n;
@@ -639,6 +666,8 @@ static int run_device_drops(shx_ctx* c, size_t n, bool trace, bool align_age = f
     a.trace_cap = c->trace_cap;
     a.trace_n = trace ? c->d_flags + 1 : nullptr;
     CU(cudaMemsetAsync(c->d_bar, 0, sizeof(GridBar), c->stream));
+    { const int rc_epoch = next_claim_epoch(c); if (rc_epoch) return rc_epoch; }
+    a.claim_epoch = c->claim_epoch;
     // every strip's reset / spawn is complete before anybody's first phase touches it
     peer_handshake_kernel<<<1, 1, 0, c->stream>>>(a.pv, a.pv.tag_base, &c->d_bar->abort);
     c->launches++;
@@ -682,6 +711,8 @@ static int run_device_drops(shx_ctx* c, size_t n, bool trace, bool align_age = f
     a.trace_cap = c->trace_cap;
     a.trace_n = (trace && done == 0) ? c->d_flags + 1 : nullptr;
     CU(cudaMemsetAsync(c->d_bar, 0, sizeof(GridBar), c->stream));
+    { const int rc_epoch = next_claim_epoch(c); if (rc_epoch) return rc_epoch; }
+    a.claim_epoch = c->claim_epoch;
     void* args[] = {&a};
     size_t take;
     if (left <= 64 && !c->forced_shape) {
@@ -702,6 +733,7 @@ static int run_device_drops(shx_ctx* c, size_t n, bool trace, bool align_age = f
       CU(cudaLaunchCooperativeKernel(ls.kernel, dim3(grid), dim3(block), args, descend_smem(block), c->stream));
     }
     c->launches++;
+    CU(cudaMemcpyAsync(c->d_flags + 2, &c->d_bar->abort, sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
     done += take;
   }
   return SHX_OK;
@@ -1156,7 +1188,7 @@ int shx_peer_attach(shx_ctx* c, const shx_peer_handles* all) {
         p[k] = static_cast<char*>(base);
       }
     }
-    c->pv.hq[r] = reinterpret_cast<int2*>(p[0] + off[0]);
+    c->pv.hq[r] = reinterpret_cast<int4*>(p[0] + off[0]);
     c->pv.rec[r] = reinterpret_cast<CellRec*>(p[1] + off[1]);
     c->pv.inbox[r] = reinterpret_cast<unsigned long long*>(p[2] + off[2]);
   }

@@ -31,7 +31,7 @@ __device__ __forceinline__ shx_drop make_drop(float x, float y, const MapView& m
   }
   float h = 0.0f;  // map.height() of a missing cell (cellpool.h:433-437)
   if (!oob) {
-    const int2 hv = m.hq[(ix - m.xlo) * m.size + iy];
+    const int4 hv = m.hq[(ix - m.xlo) * m.size + iy];
     h = sequential ? __int_as_float(hv.x) : h_to_float(hv.x);
   }
   if (!above_tenth(h)) {  // world.h:71-72  (double)h < 0.1
@@ -113,12 +113,12 @@ __global__ void unpack_tile_kernel(const TileArgs a, const shx_cell* __restrict_
     const size_t i = (size_t)(x - a.m.xlo) * a.m.size + y;
     reinterpret_cast<float4*>(a.m.rec + i)[0] = make_float4(lo.y, lo.z, lo.w, hi.w);
     if (a.sequential) {
-      a.m.hq[i] = make_int2(__float_as_int(lo.x), 0);
+      a.m.hq[i] = make_int4(__float_as_int(lo.x), 0, 0, 0);
       reinterpret_cast<float4*>(a.m.rec + i)[1] = make_float4(hi.x, hi.y, hi.z, 0.0f);
     } else {
       if (!(fabsf(lo.x) < 31.0f) || !(fabsf(hi.x) < 4096.0f)) *a.error_flag = 1;
       const int32_t q = h_quantize(lo.x);
-      a.m.hq[i] = make_int2(q, q);
+      a.m.hq[i] = make_int4(q, q, 0, 0);
       reinterpret_cast<int4*>(a.m.rec + i)[1] = make_int4(t_quantize(hi.x), t_quantize(hi.y), t_quantize(hi.z), 0);
     }
   }
@@ -133,7 +133,7 @@ __global__ void pack_tile_kernel(const TileArgs a, shx_cell* __restrict__ aos) {
     const size_t i = (size_t)(x - a.m.xlo) * a.m.size + y;
     const float4 f = reinterpret_cast<const float4*>(a.m.rec + i)[0];
     const int4 t = reinterpret_cast<const int4*>(a.m.rec + i)[1];
-    const int2 hv = a.m.hq[i];
+    const int2 hv = *reinterpret_cast<const int2*>(a.m.hq + i);
     float4 lo, hi;
     if (a.sequential) {
       lo = make_float4(__int_as_float(hv.x), f.x, f.y, f.z);
@@ -230,10 +230,10 @@ __global__ void synth_fill_kernel(const MapView m, int sequential, uint32_t seed
     reinterpret_cast<int4*>(m.rec + i)[0] = make_int4(0, 0, 0, 0);
     reinterpret_cast<int4*>(m.rec + i)[1] = make_int4(0, 0, 0, 0);
     if (sequential) {
-      m.hq[i] = make_int2(__float_as_int(h), 0);
+      m.hq[i] = make_int4(__float_as_int(h), 0, 0, 0);
     } else {
       const int32_t q = h_quantize(h);
-      m.hq[i] = make_int2(q, q);
+      m.hq[i] = make_int4(q, q, 0, 0);
     }
   }
 }
@@ -243,27 +243,28 @@ __global__ void synth_fill_kernel(const MapView m, int sequential, uint32_t seed
 // each side.  Cascade transfers of drops on the strip's boundary rows land in those halo rows;
 // `halo_ref` remembers what the halo held at the last refresh, so (current - ref) is exactly the
 // integer amount this strip owes the owner.  Outside a run both planes are equal: plane 0 is used.
-__global__ void strip_halo_delta_kernel(const int2* cur, const int32_t* ref, int32_t* out, size_t n) {
+__global__ void strip_halo_delta_kernel(const int4* cur, const int32_t* ref, int32_t* out, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     out[i] = cur[i].x - ref[i];
 }
-__global__ void strip_add_rows_kernel(int2* h, const int32_t* delta, size_t n) {
+__global__ void strip_add_rows_kernel(int4* h, const int32_t* delta, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int32_t v = delta[i];
     if (v) {
-      int2 c = h[i];
+      int2* hp = reinterpret_cast<int2*>(h + i);  // the two height words; the claim words are left alone
+      int2 c = *hp;
       c.x += v; c.y += v;
-      h[i] = c;
+      *hp = c;
     }
   }
 }
-__global__ void strip_get_rows_kernel(const int2* h, int32_t* out, size_t n) {
+__global__ void strip_get_rows_kernel(const int4* h, int32_t* out, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = h[i].x;
 }
-__global__ void strip_set_rows_kernel(int2* h, int32_t* ref, const int32_t* src, size_t n) {
+__global__ void strip_set_rows_kernel(int4* h, int32_t* ref, const int32_t* src, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int32_t v = src[i];
-    h[i] = make_int2(v, v);
+    *reinterpret_cast<int2*>(h + i) = make_int2(v, v);
     ref[i] = v;
   }
 }
@@ -288,7 +289,7 @@ __global__ void strip_pack_migrants_kernel(const shx_drop* drops, unsigned n, sh
 //   then rows*size halo deltas (what this strip moved into its copy of the neighbour's edge rows)
 //   then rows*size edge rows (what this strip's own edge rows hold now)
 constexpr int kMsgHeader = 8;
-__global__ void strip_msg_rows_kernel(const int2* halo, const int32_t* ref, const int2* edge, int32_t* out_delta, int32_t* out_edge,
+__global__ void strip_msg_rows_kernel(const int4* halo, const int32_t* ref, const int4* edge, int32_t* out_delta, int32_t* out_edge,
                                       size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     out_delta[i] = halo[i].x - ref[i];
@@ -308,18 +309,31 @@ __global__ void strip_msg_migrants_kernel(const shx_drop* drops, unsigned n, int
 }
 // The owner's edge rows take the neighbour's deltas; this strip's copy of the neighbour's edge rows
 // becomes what the neighbour holds once IT has taken this strip's deltas: its rows as sent + ours.
-__global__ void strip_msg_apply_kernel(int2* halo, int32_t* ref, int2* edge, const int32_t* in_delta, const int32_t* in_edge, size_t n) {
+__global__ void strip_msg_apply_kernel(int4* halo, int32_t* ref, int4* edge, const int32_t* in_delta, const int32_t* in_edge, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int32_t v = in_edge[i] + (halo[i].x - ref[i]);
-    halo[i] = make_int2(v, v);
+    *reinterpret_cast<int2*>(halo + i) = make_int2(v, v);
     ref[i] = v;
     const int32_t dv = in_delta[i];
     if (dv) {
-      int2 c = edge[i];
+      int2* ep = reinterpret_cast<int2*>(edge + i);
+      int2 c = *ep;
       c.x += dv; c.y += dv;
-      edge[i] = c;
+      *ep = c;
     }
   }
+}
+
+// claim words of every stored cell back to zero (when the launch epoch of the claim keys wraps)
+__global__ void clear_claims_kernel(int4* hq, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    reinterpret_cast<int2*>(hq + i)[1] = make_int2(0, 0);
+}
+
+// the two height words of every stored cell, densely (shx_download_raw)
+__global__ void copy_heights_kernel(const int4* hq, int2* out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = *reinterpret_cast<const int2*>(hq + i);
 }
 
 }  // namespace shx

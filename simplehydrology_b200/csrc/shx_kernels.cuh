@@ -1,7 +1,7 @@
 // shx CUDA kernels (sm_100a).  Layout in HBM (per context, rows [xlo, xlo+nrows) of the map),
 // index i = (x - xlo)*size + y (x-major like the reference, math.h:11-14, but one global plane
 // instead of 512^2 tiles):
-//   hq   int2 per cell: the two Q5.26 height planes interleaved {plane0, plane1}.  A phase reads
+//   hq   int4 per cell: the two Q5.26 height planes and the two claim words {plane0, plane1, claim0, claim1}.  A phase reads
 //        plane p&1 and adds into plane (p+1)&1 (see descend_lockstep); interleaving puts both in
 //        the same 32-byte sector, so the adds hit sectors the phase has just read.
 //   rec  32-byte record per cell = one L2 sector:
@@ -19,7 +19,7 @@ struct __align__(32) CellRec {
 };
 
 struct MapView {
-  int2* hq;
+  int4* hq;  // {height plane 0, height plane 1, claim word of even phases, claim word of odd phases}
   CellRec* rec;
   int size;        // cells per side of the whole map
   int xlo, nrows;  // stored rows
@@ -38,7 +38,7 @@ struct GridBar {
   // active"; both monotonically increasing over the launch (zeroed by the host before it)
   unsigned long long word[2];
   unsigned max_steps;  // longest drop of this launch == number of phases that had a live drop
-  unsigned abort;      // peer mode: a peer did not show up in time
+  unsigned abort;      // 1: peer mode, a peer did not show up in time; 2: more than kMaxPhases phases
   // peer mode: {phase tag | box-wide active sum << 32}, stored by the publishing CTA once every GPU has arrived
   unsigned long long release[2];
 };
@@ -49,7 +49,7 @@ struct GridBar {
 // schedule -- and therefore the result -- is exactly the single-GPU one.
 constexpr int kMaxPeers = 8;
 struct PeerView {
-  int2* hq[kMaxPeers];                  // strip r holds rows [r*rows, (r+1)*rows)
+  int4* hq[kMaxPeers];                  // strip r holds rows [r*rows, (r+1)*rows)
   CellRec* rec[kMaxPeers];
   unsigned long long* inbox[kMaxPeers]; // rank r's inbox: [parity][sender] words {phase+1 | sum << 32}
   int shift, mask;                      // rows per strip = 1 << shift
@@ -64,6 +64,7 @@ struct DescendArgs {
   shx_drop* drops;
   unsigned ndrops;
   unsigned align_age;  // != 0: drops with age > 0 wait for the phase equal to their age
+  unsigned claim_epoch;  // 1..15, top bits of every claim key of this launch (stale keys of earlier launches lose)
   GridBar* bar;
   unsigned long long* stats;
   float* trace;  // 7 floats per Drop::descend call of drop 0, or null
@@ -240,6 +241,26 @@ __device__ __forceinline__ float ord2f(unsigned u) {
 }
 
 
+// Same-cell exclusion.  A phase reads frozen heights, so two drops standing on one cell would both
+// erode it by the full amount -- over-erosion that feeds on itself in busy river cells (a 2048^2 map
+// ran away within 25 calls without this).  Of the drops on one cell only the holder of the highest
+// key steps in a phase; the others wait.  Keys are claimed one phase ahead with atomicMax on the
+// cell's claim word of the NEXT phase's parity.  The two claim words sit next to the two height words
+// of the cell (one 16-byte int4 per cell): the word a drop claims belongs to a sector its gather has
+// just pulled into L2, and the word it checks arrives with its centre height.  (In a plane of their
+// own the claims cost +3.3 ms per 8192^2 cycle: every claim was a DRAM read-modify-write.)
+//   key = {launch epoch : 4 | phase tag : 12 | phases waited so far, saturating : 3 | state hash : 13}
+// i.e. longest waiting first, then an order-independent pseudo-random choice; equal keys all step.
+// The epoch makes the keys of earlier launches lose; the host clears the words when it wraps.
+constexpr int kWaitedShift = 16;       // SHX_DROP_WAITED_SHIFT
+constexpr unsigned kMaxPhases = 4000;  // the tag has 12 bits
+__device__ __forceinline__ unsigned claim_key(unsigned epoch, unsigned tag, const DropRegs& d) {
+  unsigned h = __float_as_uint(d.px) * 0x9E3779B1u ^ __float_as_uint(d.py) * 0x85EBCA77u ^ (unsigned)d.age * 0xC2B2AE3Du;
+  h ^= h >> 15;
+  const unsigned waited = ((unsigned)d.flags >> kWaitedShift) & 7u;
+  return (epoch << 28) | (tag << 16) | (waited << 13) | (h & 0x1FFFu);
+}
+
 // ---------------------------------------------------------------------------------------------
 // K3: batched lock-step descend.  One thread per drop, drop state in registers, the 3x3 block of
 // the current phase in shared memory.  Phase p:
@@ -290,12 +311,17 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
   int* const H = reinterpret_cast<int*>(a.m.hq);
   // cell (x, y) -> its pair of height words / its record.  Peer mode: the strip x >> shift owns it.
   auto h_at = [&](int x, int y) -> int* {
-    if (kPeer) return reinterpret_cast<int*>(a.pv.hq[x >> a.pv.shift]) + 2 * ((x & a.pv.mask) * size + y);
-    return H + 2 * ((x - a.m.xlo) * size + y);
+    if (kPeer) return reinterpret_cast<int*>(a.pv.hq[x >> a.pv.shift]) + 4 * ((x & a.pv.mask) * size + y);
+    return H + 4 * ((x - a.m.xlo) * size + y);
   };
   auto rec_at = [&](int x, int y) -> CellRec* {
     if (kPeer) return a.pv.rec[x >> a.pv.shift] + ((x & a.pv.mask) * size + y);
     return a.m.rec + ((x - a.m.xlo) * size + y);
+  };
+  auto claim_at = [&](int x, int y) -> unsigned* { return reinterpret_cast<unsigned*>(h_at(x, y)) + 2; };
+  auto claim_max = [&](unsigned* p, unsigned key, int x) {
+    if (kPeer && (x >> a.pv.shift) != a.pv.rank) { atomicMax_system(p, key); s_remote = 1u; }
+    else atomicMax(p, key);
   };
   // Integer adds.  Peer mode: every add into a strip is performed by the L2 of the GPU that holds it;
   // the owner uses plain device-scope REDs, the others system-scope ones over NVLink, and a CTA
@@ -345,6 +371,14 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
     }                                                                                                     \
   } while (0)
 
+  // every drop that is awake in phase 0 claims its cell (tag 1, parity 0); barrier number 0
+  if (alive) claim_max(claim_at((int)d.px, (int)d.py), claim_key(a.claim_epoch, 1u, d), (int)d.px);
+  {
+    const unsigned block_sum = (unsigned)__syncthreads_count(alive || asleep);
+    if (kPeer) peer_barrier_sum(a.bar, a.pv, 0u, block_sum, &s_total, &s_remote, bar_hi0, bar_hi1);
+    else grid_barrier_sum(a.bar, 0u, block_sum, &s_total, bar_hi0, bar_hi1);
+  }
+
   for (unsigned phase = 0;; ++phase) {
     const int rpar = (int)(phase & 1u), wpar = rpar ^ 1;
     const int cur = rpar * 8, prev = wpar * 8;
@@ -387,7 +421,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
             if (ok) got[g] = __ldcg(h_at(sx + co_dx, sy + co_dy) + rpar);  // coordinates are only valid when ok
           } else {
             const int c = __shfl_sync(0xffffffffu, cidx, src & 31);
-            got[g] = ok ? __ldcg(H + 2 * (c + co_off) + rpar) : 0;
+            got[g] = ok ? __ldcg(H + 4 * (c + co_off) + rpar) : 0;
           }
         }
         if (alive) fld = __ldg(reinterpret_cast<const float4*>(rec_at(ix, iy)));
@@ -398,14 +432,19 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
         }
       }
     } else if (alive) {
-      const int* c = H + 2 * cidx + rpar;
+      const int* c = H + 4 * cidx + rpar;
 #pragma unroll
       for (int k = 0; k < 9; k++) {
         const int off = (k / 3 - 1) * size + (k % 3 - 1);
-        v[k] = ((inb >> k) & 1u) ? __ldcg(c + 2 * off) : 0;
+        v[k] = ((inb >> k) & 1u) ? __ldcg(c + 4 * off) : 0;
       }
       fld = __ldg(reinterpret_cast<const float4*>(a.m.rec + cidx));
     }
+
+    // whose turn is it on this cell?  (claimed during the previous phase, complete since its barrier)
+    unsigned held = 0u;
+    if (alive) held = __ldcg(claim_at(ix, iy) + rpar);
+    const bool turn = alive && held == claim_key(a.claim_epoch, phase + 1u, d);
 
     if (dC_prev | (int)dmask_prev) {  // catch-up of the previous phase's deltas
       if (dC_prev && !SHX_EXP(2)) add32(h_at(pix, piy) + wpar, dC_prev, pix);
@@ -423,8 +462,17 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
 
     if (kCoop) __syncwarp();  // the block rows written by the other lanes of the warp are complete
 
-    if (alive) {
+    if (alive && !turn) {  // another drop has the cell: wait, and ask again for the next phase
+      const unsigned waited = ((unsigned)d.flags >> kWaitedShift) & 7u;
+      d.flags = (d.flags & ~(7 << kWaitedShift)) | (int)((waited < 7u ? waited + 1u : 7u) << kWaitedShift);
+      claim_max(claim_at(ix, iy) + wpar, claim_key(a.claim_epoch, phase + 2u, d), ix);
+    }
+    if (asleep && (unsigned)d.age == phase + 1u)  // wakes up in the next phase
+      claim_max(claim_at((int)d.px, (int)d.py) + wpar, claim_key(a.claim_epoch, phase + 2u, d), (int)d.px);
+
+    if (turn) {
       steps++;
+      d.flags &= ~(7 << kWaitedShift);
 #pragma unroll
       for (int k = 0; k < 9; k++) {
         if (kCoop) v[k] = s_B[k];
@@ -508,7 +556,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
         const int q = h_quantize(mv.dheight);
         dC += q;
         alive = false;
-        atomicMax(&a.bar->max_steps, steps);
+        atomicMax(&a.bar->max_steps, phase + 1u);
         stat_add(a.stats, (d.flags & SHX_DROP_DONE_AGE) ? ST_TERM_AGE : ST_TERM_VOL, 1ull);
         stat_add(a.stats, ST_FX_DEPOSITED, (unsigned long long)(long long)q);
         stat_add(a.stats, ST_FX_SED_DEPOSITED, (unsigned long long)l_quantize(d.sed));
@@ -541,7 +589,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
         fx_inflation += l_quantize(d.sed) - l_quantize(carried);
         if (mv.oob) {  // water.h:139-142
           alive = false;
-          atomicMax(&a.bar->max_steps, steps);
+          atomicMax(&a.bar->max_steps, phase + 1u);
           stat_add(a.stats, ST_TERM_OOB, 1ull);
           stat_add(a.stats, ST_FX_SED_OOB, (unsigned long long)l_quantize(d.sed));
           d.vol = 0.0f;
@@ -549,11 +597,12 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
         } else {
           d.age++;                      // water.h:153
           d.flags |= SHX_DROP_CASCADE;  // water.h:151, executed at the start of the next phase
+          if (kPeer || (nix >= a.m.row0 && nix < a.m.row1)) claim_max(claim_at(nix, niy) + wpar, claim_key(a.claim_epoch, phase + 2u, d), nix);
           if (!kPeer && (nix < a.m.row0 || nix >= a.m.row1)) {  // left the strip: hand over (cascade still owed)
             const bool tolo = nix < a.m.row0;
             d.flags = (d.flags & ~SHX_DROP_ALIVE) | (tolo ? SHX_DROP_MIGRATE_LO : SHX_DROP_MIGRATE_HI);
             alive = false;
-            atomicMax(&a.bar->max_steps, steps);
+            atomicMax(&a.bar->max_steps, phase + 1u);
             stat_add(a.stats, tolo ? ST_MIGRATED_LO : ST_MIGRATED_HI, 1ull);
           }
         }
@@ -579,8 +628,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
 #endif
     const unsigned block_sum = (unsigned)__syncthreads_count(alive || asleep || (dC_prev | (int)dmask_prev));
     SHX_T(5);
-    const unsigned total = kPeer ? peer_barrier_sum(a.bar, a.pv, phase, block_sum, &s_total, &s_remote, bar_hi0, bar_hi1)
-                                 : grid_barrier_sum(a.bar, phase, block_sum, &s_total, bar_hi0, bar_hi1);
+    const unsigned total = kPeer ? peer_barrier_sum(a.bar, a.pv, phase + 1u, block_sum, &s_total, &s_remote, bar_hi0, bar_hi1)
+                                 : grid_barrier_sum(a.bar, phase + 1u, block_sum, &s_total, bar_hi0, bar_hi1);
     SHX_T(6);
 #ifdef SHX_PHASE_TIMING
     if (gid == 0 && alive) {
@@ -590,6 +639,10 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
 #endif
     if (total == 0u) {  // every termination's atomicMax happened before the barrier just passed
       if (gid == 0) stat_add(a.stats, ST_PHASES, (unsigned long long)__ldcg(&a.bar->max_steps));
+      break;
+    }
+    if (phase + 2u >= kMaxPhases) {  // the claim tag would wrap: give up (the host reports SHX_ERR_RANGE)
+      if (gid == 0) a.bar->abort = 2u;
       break;
     }
   }
@@ -654,7 +707,7 @@ __global__ void descend_sequential_kernel(const SequentialArgs a) {
         const int x = ix + k / 3 - 1, y = iy + k % 3 - 1;
         const bool in = x >= 0 && y >= 0 && x < size && y < size;
         inb |= in ? (1u << k) : 0u;
-        B[k] = in ? H[2 * (cidx + (k / 3 - 1) * size + (k % 3 - 1))] : 0.0f;
+        B[k] = in ? H[4 * (cidx + (k / 3 - 1) * size + (k % 3 - 1))] : 0.0f;
       }
       CellRec* rec = a.m.rec + cidx;
       const float4 fld = *reinterpret_cast<const float4*>(rec);
@@ -681,7 +734,7 @@ __global__ void descend_sequential_kernel(const SequentialArgs a) {
 #pragma unroll
             for (int k = 1; k < 9; k++) h2 = (k == (ddx + 1) * 3 + (ddy + 1)) ? B[k] : h2;
           } else {
-            h2 = H[2 * (nix * size + niy)];
+            h2 = H[4 * (nix * size + niy)];
           }
         }
         float carried;
@@ -698,7 +751,7 @@ __global__ void descend_sequential_kernel(const SequentialArgs a) {
       }
 #pragma unroll
       for (int k = 0; k < 9; k++)
-        if (inb & (1u << k)) H[2 * (cidx + (k / 3 - 1) * size + (k % 3 - 1))] = B[k];
+        if (inb & (1u << k)) H[4 * (cidx + (k / 3 - 1) * size + (k % 3 - 1))] = B[k];
       if (!(d.flags & SHX_DROP_ALIVE)) {
         if (d.flags & SHX_DROP_DONE_OOB) {
           a.stats[ST_TERM_OOB] += 1ull;

@@ -16,8 +16,8 @@ struct ViewArgs {
 };
 
 __device__ __forceinline__ float view_height(const ViewArgs& a, int x, int y) {
-  const int2 v = __ldg(a.m.hq + (size_t)(x - a.m.xlo) * a.m.size + y);
-  return a.sequential ? __int_as_float(v.x) : h_to_float(v.x);
+  const int v = __ldg(reinterpret_cast<const int*>(a.m.hq + (size_t)(x - a.m.xlo) * a.m.size + y));  // plane 0
+  return a.sequential ? __int_as_float(v) : h_to_float(v);
 }
 
 // quad::updatenode for every node of the owned rows.  out: 12 floats per cell {position, normal,
@@ -79,12 +79,12 @@ __global__ void view_maps_kernel(const ViewArgs a, float4* __restrict__ out, con
   const size_t off = (size_t)(a.m.row0 - a.m.xlo) * a.m.size;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncells; i += (size_t)gridDim.x * blockDim.x) {
     const float4 f = __ldg(reinterpret_cast<const float4*>(a.m.rec + off + i));  // discharge momentumx momentumy rootdensity
-    const int2 hv = __ldg(a.m.hq + off + i);
+    const int hv = __ldg(reinterpret_cast<const int*>(a.m.hq + off + i));
     float4 o;
     o.x = shx_erff(0.4f * f.x);
     o.y = 0.5f * (1.0f + shx_erff(f.y));
     o.z = 0.5f * (1.0f + shx_erff(f.z));
-    o.w = a.sequential ? __int_as_float(hv.x) : h_to_float(hv.x);
+    o.w = a.sequential ? __int_as_float(hv) : h_to_float(hv);
     out[i] = o;
   }
 }

@@ -90,7 +90,8 @@ def test_check2_mass_ledger_at_full_size(mapsize, cycles):
         for st in (st1, st2):
             assert st.spawned + st.rejected == mapsize * mapsize * cycles
             assert st.spawned == st.term_age + st.term_vol + st.term_oob
-            assert st.phases <= 502
+            assert st.steps <= 502 * st.spawned  # water.h:74: at most maxAge + 2 descend calls per drop
+            assert 502 <= st.phases < 1000       # plus the phases drops spent waiting for a shared cell
 
 
 def _metrics(a, b, init):

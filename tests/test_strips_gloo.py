@@ -60,6 +60,9 @@ def worker(rank, world, port, out_dir, mode="rounds"):
             ex.erode(CYCLES, seed=11)
             rounds.append(ex.rounds)
         accumulate()
+    # discharge as a user sees it after NCYC calls (the flush calls below run extra EMAs); heights are compared
+    # after the flush, when every drop has delivered its sediment
+    field_user = b.ls.field()[b.row0:b.row1].copy()
     if mode == "cycle":  # march what is still waiting, so that every drop is accounted for
         assert ex.in_flight() > 0
         while ex.in_flight():
@@ -77,7 +80,7 @@ def worker(rank, world, port, out_dir, mode="rounds"):
     if f_hi is not None:
         halo_ok &= np.array_equal(h[b._halo_rows(1)].ravel(), f_hi.numpy())
     planes_ok = np.array_equal(b.ls.height_q(0)[b.row0:b.row1], b.ls.height_q(1)[b.row0:b.row1])
-    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), h=h[b.row0:b.row1], field=b.ls.field()[b.row0:b.row1],
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), h=h[b.row0:b.row1], field=field_user,
              ledger=np.array([after - before, tot.fx_deposited - tot.fx_eroded, tot.spawned, tot.term_age + tot.term_vol + tot.term_oob,
                               tot.steps, int(halo_ok), int(planes_ok), max(rounds)], np.int64))
     dist.barrier()
@@ -114,8 +117,12 @@ def test_strip_exchange_conserves_and_accounts(world, mode, tmp_path):
         ls.erode(CYCLES, 11, c)
     d1 = (ls.height_q(0) - h_init).astype(np.float64).ravel()
     dk = (h - h_init).astype(np.float64).ravel()
-    assert np.corrcoef(d1, dk)[0, 1] > 0.9
-    assert np.corrcoef(ls.field()[..., 0].ravel(), field[..., 0].ravel())[0, 1] > 0.9
+    # stated bounds: 0.9 for the exchange rounds, 0.85 for one exchange per call (up to a third of a call's drops of
+    # this small, steep world are still waiting at a border when the maps are compared)
+    cd, cf = np.corrcoef(d1, dk)[0, 1], np.corrcoef(ls.field()[..., 0].ravel(), field[..., 0].ravel())[0, 1]
+    print(f"world {world} {mode}: corr(dh) {cd:.3f} corr(discharge) {cf:.3f}")
+    bound = 0.85 if mode == "cycle" else 0.9
+    assert cd > bound and cf > bound
 
 
 def test_single_strip_equals_plain_erode(tmp_path):
