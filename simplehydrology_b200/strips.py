@@ -272,7 +272,7 @@ class GpuStrip:
         self.dev = torch.device("cuda", device)
         whole = world == 1
         nodes = (tiles // world) * tiles
-        self.cap = max(4096, 2 * nodes * drops_per_node)  # spawned + carried-over drops
+        self.cap = max(4096, 4 * nodes * drops_per_node)  # spawned + carried-over drops (narrow strips carry more than they spawn)
         self.W = shx.World(params=p, device=device, row0=0 if whole else self.row0, row1=0 if whole else self.row1, halo=halo,
                            max_drops=self.cap, **world_kw)
         self.has_lo, self.has_hi = rank > 0, rank < world - 1
