@@ -279,9 +279,10 @@ __device__ __forceinline__ unsigned claim_key(unsigned epoch, unsigned tag, cons
 // kCoop selects how the 3x3 block is gathered.  With one load per lane and cell, every lane of a
 // load instruction touches its own 128-byte line and the SM's L1TEX pipe replays the instruction
 // once per line (~2 cycles each): at 28 resident warps per SM that replay time, not DRAM or L2
-// bandwidth, bounds the phase.  The cooperative gather lets nine lanes fetch the nine cells of ONE
-// drop (three drops per instruction): three lines per drop instead of nine lane-wavefronts; the
-// values travel through shared memory to the lane that owns the drop.
+// bandwidth, bounds the phase.  The cooperative gather lets eight lanes fetch the eight neighbour
+// cells of ONE drop (four drops per instruction) while the owner fetches its centre cell -- heights
+// and claim words -- with one 16-byte load: three lines per drop instead of nine lane-wavefronts;
+// the values travel through shared memory to the lane that owns the drop.
 //
 // Shared memory per thread: s_B[9] block heights (thread-major, stride 9: conflict-free both for
 // the owner's sequential reads and for the cooperative stores), s_D[2][8] neighbour deltas of this
@@ -300,9 +301,10 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
   int32_t* s_B = s_mem + tid * 9;                               // s_B[k]
   int32_t* s_D = s_mem + 9 * nt + tid;                          // s_D[(buf*8 + j)*nt]
   uint2* s_S = reinterpret_cast<uint2*>(s_mem + 25 * nt) + tid; // s_S[r*nt]
-  // cooperative gather: lane -> (which of 3 drops of a group, which of its 9 cells)
+  // cooperative gather: lane -> (which of 4 drops of a group, which of its 8 neighbour cells); the
+  // centre cell comes with the owner's own 16-byte load of {heights, claim words}
   const int lane = tid & 31;
-  const int co_k = lane % 9, co_sub = lane / 9;
+  const int co_sub = lane >> 3, co_k = (lane & 7) + ((lane & 7) >> 2);  // block index 0..8 without 4
   const int co_dx = co_k / 3 - 1, co_dy = co_k % 3 - 1;
   const int co_off = co_dx * a.m.size + co_dy;
   int32_t* const s_Bw = s_mem + (tid - lane) * 9;               // first drop of this warp
@@ -405,31 +407,34 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
                          ((xp & ym) << 6) | (xp << 7) | ((xp & yp) << 8);
     int v[9];
     float4 fld = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    unsigned held = 0u;
     if (kCoop) {
-      // 11 groups of 3 drops; lane (sub, k) loads cell k of drop 3g+sub of this warp into its s_B row
+      // 8 groups of 4 drops; lane (sub, k) loads neighbour cell k of drop 4g+sub of this warp into its s_B row
       const unsigned meta = alive ? (inb | 0x200u) : 0u;
       if (__any_sync(0xffffffffu, alive)) {
-        int got[11];
+        int got[8];
 #pragma unroll
-        for (int g = 0; g < 11; g++) {
-          const int src = g * 3 + co_sub;
-          const unsigned m = __shfl_sync(0xffffffffu, meta, src & 31);
-          const bool ok = co_sub < 3 && src < 32 && ((m >> co_k) & 1u) && (m & 0x200u);
+        for (int g = 0; g < 8; g++) {
+          const int src = g * 4 + co_sub;
+          const unsigned m = __shfl_sync(0xffffffffu, meta, src);
+          const bool ok = ((m >> co_k) & 1u) && (m & 0x200u);
           if (kPeer) {
-            const int sx = __shfl_sync(0xffffffffu, ix, src & 31), sy = __shfl_sync(0xffffffffu, iy, src & 31);
+            const int sx = __shfl_sync(0xffffffffu, ix, src), sy = __shfl_sync(0xffffffffu, iy, src);
             got[g] = 0;
             if (ok) got[g] = __ldcg(h_at(sx + co_dx, sy + co_dy) + rpar);  // coordinates are only valid when ok
           } else {
-            const int c = __shfl_sync(0xffffffffu, cidx, src & 31);
+            const int c = __shfl_sync(0xffffffffu, cidx, src);
             got[g] = ok ? __ldcg(H + 4 * (c + co_off) + rpar) : 0;
           }
         }
-        if (alive) fld = __ldg(reinterpret_cast<const float4*>(rec_at(ix, iy)));
-#pragma unroll
-        for (int g = 0; g < 11; g++) {
-          const int src = g * 3 + co_sub;
-          if (co_sub < 3 && src < 32) s_Bw[src * 9 + co_k] = got[g];
+        if (alive) {
+          const int4 cc = __ldcg(reinterpret_cast<const int4*>(h_at(ix, iy)));  // centre heights + claim words
+          s_B[4] = rpar ? cc.y : cc.x;
+          held = (unsigned)(rpar ? cc.w : cc.z);
+          fld = __ldg(reinterpret_cast<const float4*>(rec_at(ix, iy)));
         }
+#pragma unroll
+        for (int g = 0; g < 8; g++) s_Bw[(g * 4 + co_sub) * 9 + co_k] = got[g];
       }
     } else if (alive) {
       const int* c = H + 4 * cidx + rpar;
@@ -439,11 +444,10 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
         v[k] = ((inb >> k) & 1u) ? __ldcg(c + 4 * off) : 0;
       }
       fld = __ldg(reinterpret_cast<const float4*>(a.m.rec + cidx));
+      held = __ldcg(claim_at(ix, iy) + rpar);
     }
 
     // whose turn is it on this cell?  (claimed during the previous phase, complete since its barrier)
-    unsigned held = 0u;
-    if (alive) held = __ldcg(claim_at(ix, iy) + rpar);
     const bool turn = alive && held == claim_key(a.claim_epoch, phase + 1u, d);
 
     if (dC_prev | (int)dmask_prev) {  // catch-up of the previous phase's deltas
