@@ -112,3 +112,48 @@ def test_synth_terrain_is_normalised_and_seeded():
     c = orc.synth_terrain(256, 2)
     assert a.min() == 0.0 and a.max() == 1.0 and np.array_equal(a, b) and not np.array_equal(a, c)
     assert 0.3 < a.mean() < 0.7
+
+
+def test_drops_on_one_cell_take_turns(init_cells):
+    """Same-cell exclusion: of the drops standing on one cell only one steps per phase; the
+    others wait without ageing.  k drops spawned on the same cell therefore leave it one after another, and a
+    drop that is alone is not affected at all."""
+    p = orc.default_params(1)
+    k = 5
+    xy = np.tile(np.array([[256.25, 256.5]], np.float32), (k, 1))
+    xy += np.linspace(0.0, 0.4, k, dtype=np.float32)[:, None]  # same cell, different positions (different keys)
+    ls = orc.Ls(p)
+    ls.upload(init_cells)
+    drops, _ = ls.make_drops(xy)
+    st, _ = ls.run_drops(drops)
+    lone = orc.Ls(p)
+    lone.upload(init_cells)
+    d1, _ = lone.make_drops(xy[:1])
+    s1, _ = lone.run_drops(d1)
+    assert st.phases >= s1.phases + (k - 1)            # at least k-1 phases were spent waiting at the start
+    assert st.steps > (k - 1) * 100                    # yet every drop went its way
+    assert st.term_age + st.term_vol + st.term_oob == k
+    # without the exclusion all k step together in phase 0: fewer phases, a k-fold hit on the first cell
+    free = orc.Ls(p)
+    free.upload(init_cells)
+    free.w.contents.exclusive_cells = 0
+    d2, _ = free.make_drops(xy)
+    s2, _ = free.run_drops(d2)
+    assert s2.phases < st.phases
+    c0 = (256, 256)
+    h0 = init_cells["height"][orc.tiled_index_map(p)[c0]]
+    assert abs(free.height_q(0)[c0] * H_LSB - h0) > abs(ls.height_q(0)[c0] * H_LSB - h0) * 0.99  # no smaller hit
+
+
+def test_exclusion_keeps_order_independence(init_cells):
+    p = orc.default_params(1)
+    rng = np.random.default_rng(8)
+    xy = np.repeat(rng.integers(100, 400, size=(40, 2)).astype(np.float32), 6, axis=0)  # six drops per cell
+    xy += rng.uniform(0.0, 0.9, size=xy.shape).astype(np.float32)
+    out = []
+    for perm in (np.arange(len(xy)), rng.permutation(len(xy))):
+        ls = orc.Ls(p)
+        ls.upload(init_cells)
+        st = ls.erode_spawnlist(xy[perm])
+        out.append((ls.height_q(0).copy(), st.as_dict()))
+    assert np.array_equal(out[0][0], out[1][0]) and out[0][1] == out[1][1]
