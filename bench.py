@@ -119,6 +119,37 @@ def time_reference(R, mapsize, drops_per_step, steps, warmup, seed=SEED):
     return total_steps, total_s
 
 
+def replica_worker(seconds, seed):
+    """one independent reference world (2048^2, its own seed) eroding for ~`seconds`; prints its particle steps and time"""
+    import numpy as np
+    R = reference_world(4, seed)
+    if R is None:
+        print("0 1.0")
+        return 0
+    rng = np.random.default_rng(seed)
+    steps, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        steps += R.erode_spawnlist(rng.integers(0, 2048, size=(2048, 2)).astype(np.float32))["steps"]
+    print(steps, time.perf_counter() - t0)
+    return 0
+
+
+def reference_replicas(ncores, seconds=6.0):
+    """The generous many-core figure: the reference loop is sequential and non-reentrant, so more
+    cores can only run more worlds -- N independent 2048^2 replicas, one process per core, aggregate steps/s."""
+    procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--replica", str(seconds), "--replica-seed", str(100 + i)],
+                              stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for i in range(ncores)]
+    total = 0.0
+    for pr in procs:
+        out, _ = pr.communicate(timeout=seconds * 10 + 120)
+        try:
+            st, dt = out.split()[-2:]
+            total += float(st) / float(dt)
+        except Exception:
+            pass
+    return total
+
+
 def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return 0
@@ -384,6 +415,13 @@ def run_cuda(args):
                     "value": nst / secs, "unit": UNIT, "cores": 1, "kind": "reference", "host_cores": os.cpu_count(),
                     "sample": f"3 x {drops} drops (of the cycle's {MAPSIZE * MAPSIZE * CYCLES}) on the same 8192^2 world through the reference's own "
                               f"Drop::descend / World::cascade (oracle/_ref), incl. reset + EMA passes; {secs:.1f} s of CPU"}
+                del R
+                ncores = os.cpu_count() or 1
+                agg = reference_replicas(ncores)
+                line["cpu_baseline"]["replicas"] = {
+                    "value": agg, "unit": UNIT, "cores": ncores,
+                    "note": "the reference loop cannot use more than one core for one world; this is N independent 2048^2 worlds, "
+                            "one process per core, ~6 s each: the generous many-core figure, not the same job"}
             else:
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "oracle/_ref not built"}
         except Exception as e:  # the baseline must never take the GPU numbers down with it
@@ -404,9 +442,13 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--e2e-mask", default="all", choices=["all", "hdm"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replica", type=float, default=0.0, help=argparse.SUPPRESS)
+    ap.add_argument("--replica-seed", type=int, default=100, help=argparse.SUPPRESS)
     ap.add_argument("--multi", default="cycle", choices=["cycle", "peer", "rounds"],
                     help="N > 1: strips exchanging once per cycle (default), peer-mapped lock step, or exchange rounds")
     args = ap.parse_args()
+    if args.replica > 0:
+        return replica_worker(args.replica, args.replica_seed)
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
