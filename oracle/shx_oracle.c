@@ -377,7 +377,7 @@ orc_ls_world* orc_ls_create(const orc_params* p) {
   w->track = (orc_track*)calloc(n, sizeof(orc_track));
   w->row0 = 0;
   w->row1 = w->size;
-  w->exclusive_cells = 1;
+  w->exclusive_cells = 2;
   return w;
 }
 
@@ -500,6 +500,9 @@ static uint32_t ls_cascade_block(const orc_params* P, int32_t* B, const int* inb
 /* Same-cell exclusion of the lock step: of the drops that stand on one cell in a phase only the holder of the
  * highest key steps, the others wait a phase (a drop reads frozen heights, so two drops eroding one cell in the
  * same phase would both take the full amount: over-erosion that feeds on itself in busy river cells).
+ * exclusive_cells == 2 (default) widens the rule to the 3x3 block: a drop also waits while a drop with a higher key
+ * stands on one of the eight cells around it, so that neighbouring cells never change in the same phase (a train of
+ * drops along a river updating all its cells at once is an explicit scheme with a factor above 1: it oscillates).
  * key = {phase tag | phases waited so far, saturating at 7 : 3 | hash of the drop's state : 13}: longest waiting
  * first, then an order-independent pseudo-random choice; drops with equal keys all step. */
 static uint32_t ls_claim_key(uint32_t tag, const orc_drop* d) {
@@ -669,9 +672,34 @@ void orc_ls_run(orc_ls_world* w, orc_drop* drops, size_t n, orc_stats* st, float
       active++;
       if (claim && !(w->align_age && (uint64_t)drops[i].age > phase * S)) {
         const size_t c = (size_t)trunc_i(drops[i].px) * size + trunc_i(drops[i].py);
-        if (claim[c] != ls_claim_key((uint32_t)phase + 1u, &drops[i])) { /* another drop has the cell this phase */
+        const uint32_t key = ls_claim_key((uint32_t)phase + 1u, &drops[i]);
+        int blocked = claim[c] != key; /* another drop has the cell this phase */
+        if (!blocked && w->exclusive_cells >= 2) { /* ... or a drop with a higher key stands on one of the 8 cells around */
+          const int x = trunc_i(drops[i].px), y = trunc_i(drops[i].py);
+          for (int dx = -1; dx <= 1; dx++)
+            for (int dy = -1; dy <= 1; dy++)
+              if ((dx || dy) && !ls_oob(w, x + dx, y + dy) && claim[(size_t)(x + dx) * size + (y + dy)] > key) blocked = 1;
+        }
+        if (blocked) {
           const int waited = (drops[i].flags >> ORC_DROP_WAITED_SHIFT) & 7;
           drops[i].flags = (drops[i].flags & ~(7 << ORC_DROP_WAITED_SHIFT)) | ((waited < 7 ? waited + 1 : 7) << ORC_DROP_WAITED_SHIFT);
+          /* A phase spent waiting is a step of the drop's life not taken: the age advances, so a call never needs
+           * more phases than maxAge + 2 however long the queues.  A drop that expires in the queue leaves its
+           * sediment where it stands (water.h:74-77). */
+          drops[i].age++;
+          if ((float)drops[i].age > w->p.maxAge) {
+            int32_t* D = deltas + 9 * (i * S);
+            for (int k = 0; k < 9; k++) D[k] = 0;
+            const int32_t q = orc_ls_quantize_height(drops[i].sediment);
+            D[4] = q;
+            dpos[2 * (i * S)] = trunc_i(drops[i].px);
+            dpos[2 * (i * S) + 1] = trunc_i(drops[i].py);
+            has[i * S] = 1;
+            local.fx_deposited += q;
+            local.fx_sed_deposited += tq(drops[i].sediment);
+            local.term_age++;
+            drops[i].flags = ORC_DROP_DONE_AGE;
+          }
           continue;
         }
         drops[i].flags &= ~(7 << ORC_DROP_WAITED_SHIFT);

@@ -118,7 +118,7 @@ __global__ void unpack_tile_kernel(const TileArgs a, const shx_cell* __restrict_
     } else {
       if (!(fabsf(lo.x) < 31.0f) || !(fabsf(hi.x) < 4096.0f)) *a.error_flag = 1;
       const int32_t q = h_quantize(lo.x);
-      a.m.hq[i] = make_int4(q, q, 0, 0);
+      a.m.hq[i] = make_int4(q, 0, q, 0);
       reinterpret_cast<int4*>(a.m.rec + i)[1] = make_int4(t_quantize(hi.x), t_quantize(hi.y), t_quantize(hi.z), 0);
     }
   }
@@ -233,7 +233,7 @@ __global__ void synth_fill_kernel(const MapView m, int sequential, uint32_t seed
       m.hq[i] = make_int4(__float_as_int(h), 0, 0, 0);
     } else {
       const int32_t q = h_quantize(h);
-      m.hq[i] = make_int4(q, q, 0, 0);
+      m.hq[i] = make_int4(q, 0, q, 0);
     }
   }
 }
@@ -251,10 +251,9 @@ __global__ void strip_add_rows_kernel(int4* h, const int32_t* delta, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int32_t v = delta[i];
     if (v) {
-      int2* hp = reinterpret_cast<int2*>(h + i);  // the two height words; the claim words are left alone
-      int2 c = *hp;
-      c.x += v; c.y += v;
-      *hp = c;
+      int4 c = h[i];  // {h0, claim0, h1, claim1}: outside a launch the claim words carry nothing that matters
+      c.x += v; c.z += v;
+      h[i] = c;
     }
   }
 }
@@ -264,7 +263,9 @@ __global__ void strip_get_rows_kernel(const int4* h, int32_t* out, size_t n) {
 __global__ void strip_set_rows_kernel(int4* h, int32_t* ref, const int32_t* src, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int32_t v = src[i];
-    *reinterpret_cast<int2*>(h + i) = make_int2(v, v);
+    int4 c = h[i];
+    c.x = v; c.z = v;
+    h[i] = c;
     ref[i] = v;
   }
 }
@@ -311,15 +312,16 @@ __global__ void strip_msg_migrants_kernel(const shx_drop* drops, unsigned n, int
 // becomes what the neighbour holds once IT has taken this strip's deltas: its rows as sent + ours.
 __global__ void strip_msg_apply_kernel(int4* halo, int32_t* ref, int4* edge, const int32_t* in_delta, const int32_t* in_edge, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const int32_t v = in_edge[i] + (halo[i].x - ref[i]);
-    *reinterpret_cast<int2*>(halo + i) = make_int2(v, v);
+    int4 hc = halo[i];
+    const int32_t v = in_edge[i] + (hc.x - ref[i]);
+    hc.x = v; hc.z = v;
+    halo[i] = hc;
     ref[i] = v;
     const int32_t dv = in_delta[i];
     if (dv) {
-      int2* ep = reinterpret_cast<int2*>(edge + i);
-      int2 c = *ep;
-      c.x += dv; c.y += dv;
-      *ep = c;
+      int4 c = edge[i];
+      c.x += dv; c.z += dv;
+      edge[i] = c;
     }
   }
 }
@@ -327,13 +329,20 @@ __global__ void strip_msg_apply_kernel(int4* halo, int32_t* ref, int4* edge, con
 // claim words of every stored cell back to zero (when the launch epoch of the claim keys wraps)
 __global__ void clear_claims_kernel(int4* hq, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    reinterpret_cast<int2*>(hq + i)[1] = make_int2(0, 0);
+  {
+    int4 c = hq[i];
+    c.y = 0; c.w = 0;
+    hq[i] = c;
+  }
 }
 
 // the two height words of every stored cell, densely (shx_download_raw)
 __global__ void copy_heights_kernel(const int4* hq, int2* out, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    out[i] = *reinterpret_cast<const int2*>(hq + i);
+  {
+    const int4 c = hq[i];
+    out[i] = make_int2(c.x, c.z);
+  }
 }
 
 }  // namespace shx

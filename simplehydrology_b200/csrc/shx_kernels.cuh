@@ -1,7 +1,7 @@
 // shx CUDA kernels (sm_100a).  Layout in HBM (per context, rows [xlo, xlo+nrows) of the map),
 // index i = (x - xlo)*size + y (x-major like the reference, math.h:11-14, but one global plane
 // instead of 512^2 tiles):
-//   hq   int4 per cell: the two Q5.26 height planes and the two claim words {plane0, plane1, claim0, claim1}.  A phase reads
+//   hq   int4 per cell: the two Q5.26 height planes and the two claim words {plane0, claim0, plane1, claim1}.  A phase reads
 //        plane p&1 and adds into plane (p+1)&1 (see descend_lockstep); interleaving puts both in
 //        the same 32-byte sector, so the adds hit sectors the phase has just read.
 //   rec  32-byte record per cell = one L2 sector:
@@ -19,7 +19,7 @@ struct __align__(32) CellRec {
 };
 
 struct MapView {
-  int4* hq;  // {height plane 0, height plane 1, claim word of even phases, claim word of odd phases}
+  int4* hq;  // {height plane 0, claim word of even phases, height plane 1, claim word of odd phases}
   CellRec* rec;
   int size;        // cells per side of the whole map
   int xlo, nrows;  // stored rows
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
     if (kPeer) return a.pv.rec[x >> a.pv.shift] + ((x & a.pv.mask) * size + y);
     return a.m.rec + ((x - a.m.xlo) * size + y);
   };
-  auto claim_at = [&](int x, int y) -> unsigned* { return reinterpret_cast<unsigned*>(h_at(x, y)) + 2; };
+  auto claim_at = [&](int x, int y) -> unsigned* { return reinterpret_cast<unsigned*>(h_at(x, y)) + 1; };
   auto claim_max = [&](unsigned* p, unsigned key, int x) {
     if (kPeer && (x >> a.pv.shift) != a.pv.rank) { atomicMax_system(p, key); s_remote = 1u; }
     else atomicMax(p, key);
@@ -383,6 +383,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
 
   for (unsigned phase = 0;; ++phase) {
     const int rpar = (int)(phase & 1u), wpar = rpar ^ 1;
+    const int rw = 2 * rpar, ww = 2 * wpar;  // word of the read / write plane inside a cell {h0, claim0, h1, claim1}
     const int cur = rpar * 8, prev = wpar * 8;
     if (asleep && (unsigned)d.age <= phase) {
       asleep = false;
@@ -408,57 +409,69 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
     int v[9];
     float4 fld = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     unsigned held = 0u;
+    bool blocked = false;  // a drop with a higher key stands on one of the eight cells around
     if (kCoop) {
-      // 8 groups of 4 drops; lane (sub, k) loads neighbour cell k of drop 4g+sub of this warp into its s_B row
+      // 8 groups of 4 drops; lane (sub, k) loads neighbour cell k of drop 4g+sub of this warp -- its height
+      // and its claim word of this phase, one 8-byte load -- the height into that drop's s_B row; a
+      // claim above the drop's own key blocks the drop (one ballot per group tells the owners)
       const unsigned meta = alive ? (inb | 0x200u) : 0u;
+      const unsigned mykey = claim_key(a.claim_epoch, phase + 1u, d);
       if (__any_sync(0xffffffffu, alive)) {
-        int got[8];
+        int2 got[8];
 #pragma unroll
         for (int g = 0; g < 8; g++) {
           const int src = g * 4 + co_sub;
           const unsigned m = __shfl_sync(0xffffffffu, meta, src);
           const bool ok = ((m >> co_k) & 1u) && (m & 0x200u);
+          got[g] = make_int2(0, 0);
           if (kPeer) {
             const int sx = __shfl_sync(0xffffffffu, ix, src), sy = __shfl_sync(0xffffffffu, iy, src);
-            got[g] = 0;
-            if (ok) got[g] = __ldcg(h_at(sx + co_dx, sy + co_dy) + rpar);  // coordinates are only valid when ok
+            if (ok) got[g] = __ldcg(reinterpret_cast<const int2*>(h_at(sx + co_dx, sy + co_dy) + rw));  // coordinates are only valid when ok
           } else {
             const int c = __shfl_sync(0xffffffffu, cidx, src);
-            got[g] = ok ? __ldcg(H + 4 * (c + co_off) + rpar) : 0;
+            if (ok) got[g] = __ldcg(reinterpret_cast<const int2*>(H + 4 * (c + co_off) + rw));
           }
         }
         if (alive) {
           const int4 cc = __ldcg(reinterpret_cast<const int4*>(h_at(ix, iy)));  // centre heights + claim words
-          s_B[4] = rpar ? cc.y : cc.x;
-          held = (unsigned)(rpar ? cc.w : cc.z);
+          s_B[4] = rpar ? cc.z : cc.x;
+          held = (unsigned)(rpar ? cc.w : cc.y);
           fld = __ldg(reinterpret_cast<const float4*>(rec_at(ix, iy)));
         }
 #pragma unroll
-        for (int g = 0; g < 8; g++) s_Bw[(g * 4 + co_sub) * 9 + co_k] = got[g];
+        for (int g = 0; g < 8; g++) {
+          const int src = g * 4 + co_sub;
+          s_Bw[src * 9 + co_k] = got[g].x;
+          const unsigned key_src = __shfl_sync(0xffffffffu, mykey, src);
+          const unsigned bal = __ballot_sync(0xffffffffu, (unsigned)got[g].y > key_src);
+          if ((lane >> 2) == g) blocked = ((bal >> (8 * (lane & 3))) & 0xFFu) != 0u;
+        }
       }
     } else if (alive) {
-      const int* c = H + 4 * cidx + rpar;
+      const int* c = H + 4 * cidx + rw;
+      const unsigned mykey = claim_key(a.claim_epoch, phase + 1u, d);
 #pragma unroll
       for (int k = 0; k < 9; k++) {
         const int off = (k / 3 - 1) * size + (k % 3 - 1);
         v[k] = ((inb >> k) & 1u) ? __ldcg(c + 4 * off) : 0;
+        if (k != 4 && ((inb >> k) & 1u)) blocked |= (unsigned)__ldcg(c + 4 * off + 1) > mykey;
       }
       fld = __ldg(reinterpret_cast<const float4*>(a.m.rec + cidx));
-      held = __ldcg(claim_at(ix, iy) + rpar);
+      held = __ldcg(claim_at(ix, iy) + rw);
     }
 
     // whose turn is it on this cell?  (claimed during the previous phase, complete since its barrier)
-    const bool turn = alive && held == claim_key(a.claim_epoch, phase + 1u, d);
+    const bool turn = alive && held == claim_key(a.claim_epoch, phase + 1u, d) && !blocked;
 
     if (dC_prev | (int)dmask_prev) {  // catch-up of the previous phase's deltas
-      if (dC_prev && !SHX_EXP(2)) add32(h_at(pix, piy) + wpar, dC_prev, pix);
+      if (dC_prev && !SHX_EXP(2)) add32(h_at(pix, piy) + ww, dC_prev, pix);
       unsigned m = dmask_prev;
       while (m) {
         const int j = __ffs(m) - 1;
         m &= m - 1u;
         const int k = j + (j >> 2);
         const int kx = (k * 11) >> 5;
-        if (!SHX_EXP(2)) add32(h_at(pix + kx - 1, piy + (k - 3 * kx) - 1) + wpar, s_D[(prev + j) * nt], pix + kx - 1);
+        if (!SHX_EXP(2)) add32(h_at(pix + kx - 1, piy + (k - 3 * kx) - 1) + ww, s_D[(prev + j) * nt], pix + kx - 1);
       }
       dC_prev = 0;
       dmask_prev = 0;
@@ -466,13 +479,31 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
 
     if (kCoop) __syncwarp();  // the block rows written by the other lanes of the warp are complete
 
-    if (alive && !turn) {  // another drop has the cell: wait, and ask again for the next phase
+    if (alive && !turn) {  // a drop with a higher key has the cell or stands next to it: wait
       const unsigned waited = ((unsigned)d.flags >> kWaitedShift) & 7u;
       d.flags = (d.flags & ~(7 << kWaitedShift)) | (int)((waited < 7u ? waited + 1u : 7u) << kWaitedShift);
-      claim_max(claim_at(ix, iy) + wpar, claim_key(a.claim_epoch, phase + 2u, d), ix);
+      // A phase spent waiting is a step of the drop's life not taken: the age advances, so a launch never
+      // needs more phases than maxAge + 2 however long the queues.  A drop that expires in the queue
+      // leaves its sediment where it stands (water.h:74-77).
+      d.age++;
+      if ((float)d.age > a.P.maxAge) {
+        const int q = h_quantize(d.sed);
+        if (q && !SHX_EXP(2)) add32(h_at(ix, iy) + ww, q, ix);
+        dC_prev = q;  // the other plane gets it in the next phase, like any other delta
+        pix = ix;
+        piy = iy;
+        alive = false;
+        atomicMax(&a.bar->max_steps, phase + 1u);
+        stat_add(a.stats, ST_TERM_AGE, 1ull);
+        stat_add(a.stats, ST_FX_DEPOSITED, (unsigned long long)(long long)q);
+        stat_add(a.stats, ST_FX_SED_DEPOSITED, (unsigned long long)l_quantize(d.sed));
+        d.flags = SHX_DROP_DONE_AGE;
+      } else {
+        claim_max(claim_at(ix, iy) + ww, claim_key(a.claim_epoch, phase + 2u, d), ix);
+      }
     }
     if (asleep && (unsigned)d.age == phase + 1u)  // wakes up in the next phase
-      claim_max(claim_at((int)d.px, (int)d.py) + wpar, claim_key(a.claim_epoch, phase + 2u, d), (int)d.px);
+      claim_max(claim_at((int)d.px, (int)d.py) + ww, claim_key(a.claim_epoch, phase + 2u, d), (int)d.px);
 
     if (turn) {
       steps++;
@@ -540,7 +571,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
                 s_B[k] += s;
                 s_D[(cur + (int)j) * nt] = s;
                 dmask |= 1u << j;
-                if (!SHX_EXP(2)) add32(h_at(ix + kx - 1, iy + (k - 3 * kx) - 1) + wpar, s, ix + kx - 1);
+                if (!SHX_EXP(2)) add32(h_at(ix + kx - 1, iy + (k - 3 * kx) - 1) + ww, s, ix + kx - 1);
                 transfers++;
               }
             }
@@ -573,7 +604,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
         if (!mv.oob) {
           const int ddx = nix - ix, ddy = niy - iy;
           if (ddx >= -1 && ddx <= 1 && ddy >= -1 && ddy <= 1) hv = s_B[(ddx + 1) * 3 + (ddy + 1)];
-          else hv = __ldcg(h_at(nix, niy) + rpar);
+          else hv = __ldcg(h_at(nix, niy) + rw);
         }
         const float cap = 1.0f + a.P.entrainment * shx_erff(0.4f * fld.x);  // water.h:127, cellpool.h:242-244
         if (!SHX_EXP(1)) {  // water.h:115-117.  discharge (>= 0, low word) and momentum-x (high word)
@@ -601,7 +632,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
         } else {
           d.age++;                      // water.h:153
           d.flags |= SHX_DROP_CASCADE;  // water.h:151, executed at the start of the next phase
-          if (kPeer || (nix >= a.m.row0 && nix < a.m.row1)) claim_max(claim_at(nix, niy) + wpar, claim_key(a.claim_epoch, phase + 2u, d), nix);
+          if (kPeer || (nix >= a.m.row0 && nix < a.m.row1)) claim_max(claim_at(nix, niy) + ww, claim_key(a.claim_epoch, phase + 2u, d), nix);
           if (!kPeer && (nix < a.m.row0 || nix >= a.m.row1)) {  // left the strip: hand over (cascade still owed)
             const bool tolo = nix < a.m.row0;
             d.flags = (d.flags & ~SHX_DROP_ALIVE) | (tolo ? SHX_DROP_MIGRATE_LO : SHX_DROP_MIGRATE_HI);
@@ -612,7 +643,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
         }
         SHX_TRACE_ROW();
       }
-      if (dC && !SHX_EXP(2)) add32(h_at(ix, iy) + wpar, dC, ix);
+      if (dC && !SHX_EXP(2)) add32(h_at(ix, iy) + ww, dC, ix);
       dC_prev = dC;
       dmask_prev = dmask;
       pix = ix;

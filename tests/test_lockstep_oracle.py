@@ -115,9 +115,10 @@ def test_synth_terrain_is_normalised_and_seeded():
 
 
 def test_drops_on_one_cell_take_turns(init_cells):
-    """Same-cell exclusion: of the drops standing on one cell only one steps per phase; the
-    others wait without ageing.  k drops spawned on the same cell therefore leave it one after another, and a
-    drop that is alone is not affected at all."""
+    """Turn-taking: of the drops standing on one cell (or next to a drop with a higher key) only one
+    steps per phase; the others wait, and a phase spent waiting is a step of their life not taken.  k drops spawned
+    on the same cell therefore leave it one after another, the call still ends after maxAge + 2 phases, and a drop
+    that is alone is not affected at all."""
     p = orc.default_params(1)
     k = 5
     xy = np.tile(np.array([[256.25, 256.5]], np.float32), (k, 1))
@@ -130,8 +131,8 @@ def test_drops_on_one_cell_take_turns(init_cells):
     lone.upload(init_cells)
     d1, _ = lone.make_drops(xy[:1])
     s1, _ = lone.run_drops(d1)
-    assert st.phases >= s1.phases + (k - 1)            # at least k-1 phases were spent waiting at the start
-    assert st.steps > (k - 1) * 100                    # yet every drop went its way
+    assert st.phases == s1.phases == 502               # waiting does not prolong the call
+    assert (k - 1) * 100 < st.steps <= k * s1.steps - (k - 1)  # every drop went its way, minus the steps spent waiting
     assert st.term_age + st.term_vol + st.term_oob == k
     # without the exclusion all k step together in phase 0: fewer phases, a k-fold hit on the first cell
     free = orc.Ls(p)
@@ -139,7 +140,7 @@ def test_drops_on_one_cell_take_turns(init_cells):
     free.w.contents.exclusive_cells = 0
     d2, _ = free.make_drops(xy)
     s2, _ = free.run_drops(d2)
-    assert s2.phases < st.phases
+    assert s2.steps > st.steps
     c0 = (256, 256)
     h0 = init_cells["height"][orc.tiled_index_map(p)[c0]]
     assert abs(free.height_q(0)[c0] * H_LSB - h0) > abs(ls.height_q(0)[c0] * H_LSB - h0) * 0.99  # no smaller hit
