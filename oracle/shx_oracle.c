@@ -377,7 +377,8 @@ orc_ls_world* orc_ls_create(const orc_params* p) {
   w->track = (orc_track*)calloc(n, sizeof(orc_track));
   w->row0 = 0;
   w->row1 = w->size;
-  w->exclusive_cells = 2;
+  w->exclusive_cells = 3;
+  w->cur_damp = 1.0f;
   return w;
 }
 
@@ -580,6 +581,7 @@ static int ls_step(orc_ls_world* w, const int32_t* R, orc_drop* d, int32_t* D, i
   }
   float effD = P->depositionRate * (1.0f - root); /* :86-87 */
   if (effD < 0) effD = 0;
+  effD = effD * w->cur_damp; /* 1, or 0.5 next to a drop with a higher key (exclusive_cells == 3) */
   {
     const float g = lod * P->gravity; /* :95 */
     d->sx += (g * nx) / d->volume;
@@ -674,11 +676,15 @@ void orc_ls_run(orc_ls_world* w, orc_drop* drops, size_t n, orc_stats* st, float
         const size_t c = (size_t)trunc_i(drops[i].px) * size + trunc_i(drops[i].py);
         const uint32_t key = ls_claim_key((uint32_t)phase + 1u, &drops[i]);
         int blocked = claim[c] != key; /* another drop has the cell this phase */
-        if (!blocked && w->exclusive_cells >= 2) { /* ... or a drop with a higher key stands on one of the 8 cells around */
+        w->cur_damp = 1.0f;
+        if (!blocked && w->exclusive_cells >= 2) { /* a drop with a higher key stands on one of the 8 cells around */
           const int x = trunc_i(drops[i].px), y = trunc_i(drops[i].py);
+          int crowded = 0;
           for (int dx = -1; dx <= 1; dx++)
             for (int dy = -1; dy <= 1; dy++)
-              if ((dx || dy) && !ls_oob(w, x + dx, y + dy) && claim[(size_t)(x + dx) * size + (y + dy)] > key) blocked = 1;
+              if ((dx || dy) && !ls_oob(w, x + dx, y + dy) && claim[(size_t)(x + dx) * size + (y + dy)] > key) crowded = 1;
+          if (crowded && w->exclusive_cells == 2) blocked = 1;     /* 2: wait */
+          else if (crowded) w->cur_damp = 0.5f;                     /* 3: step, with half the sediment exchange */
         }
         if (blocked) {
           const int waited = (drops[i].flags >> ORC_DROP_WAITED_SHIFT) & 7;

@@ -126,8 +126,10 @@ typedef struct {
   int align_age;    /* != 0: a drop of age a sleeps until phase a (drops carried over from the previous call) */
   int max_cycles_per_launch; /* orc_ls_erode: drops per node that march together (0 = 512), shx_config's field */
   int exclusive_cells; /* 1: of the drops that stand on the same cell in a phase only the holder of the highest
-                          claim key steps, the others wait for the next phase; 2 (default): a drop also waits
-                          while a higher key stands on one of the eight cells around it; 0: no turn-taking */
+                          claim key steps, the others wait for the next phase; 2: a drop also waits while a
+                          higher key stands on one of the eight cells around it; 3 (default): such a drop steps,
+                          but with half the sediment exchange; 0: no turn-taking */
+  float cur_damp;      /* internal: factor on the sediment exchange of the step being made */
   int steps_per_phase; /* S >= 1 steps between two global meetings; within a phase a drop reads the frozen
                           plane plus its OWN earlier deltas of the phase (0 is read as 1) */
 } orc_ls_world;

@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
     }
 
     // whose turn is it on this cell?  (claimed during the previous phase, complete since its barrier)
-    const bool turn = alive && held == claim_key(a.claim_epoch, phase + 1u, d) && !blocked;
+    const bool turn = alive && held == claim_key(a.claim_epoch, phase + 1u, d);
 
     if (dC_prev | (int)dmask_prev) {  // catch-up of the previous phase's deltas
       if (dC_prev && !SHX_EXP(2)) add32(h_at(pix, piy) + ww, dC_prev, pix);
@@ -617,7 +617,9 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
         }
         const float h2 = mv.oob ? oob_h2(hc) : h_to_float(hv);  // water.h:121-124
         float carried;
-        const float dh = exchange_math(hc, h2, cap, mv.effD, d, a.P, carried);  // water.h:127-136
+        // next to a drop with a higher key the exchange is halved: neighbouring cells that change in the same
+        // phase form an explicit scheme whose factor (up to 1.1 per cell) must stay below 1 in sum
+        const float dh = exchange_math(hc, h2, cap, blocked ? mv.effD * 0.5f : mv.effD, d, a.P, carried);  // water.h:127-136
         const int q = h_quantize(dh);
         dC += q;
         fx_eroded -= (long long)q;
