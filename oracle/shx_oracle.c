@@ -460,7 +460,7 @@ void orc_ls_make_drops(const orc_ls_world* w, const float* xy, size_t n, orc_dro
 /* World::cascade (world.h:90-168) on a private 3x3 integer block B (centre index 4,
  * k = (dx+1)*3 + (dy+1)); inb[k] tells which cells exist.  Transfers are quantised
  * to the height fixed point and applied to B and to the delta block D. */
-static uint32_t ls_cascade_block(const orc_params* P, int32_t* B, const int* inb, int32_t* D) {
+static uint32_t ls_cascade_block(const orc_params* P, int32_t* B, const int* inb, int32_t* D, float damp) {
   static const int order[8] = {0, 1, 2, 3, 5, 6, 7, 8}; /* world.h:94-103 in block indices */
   struct { int k; float h, d; } sn[8], tmp;
   int num = 0;
@@ -486,7 +486,7 @@ static uint32_t ls_cascade_block(const orc_params* P, int32_t* B, const int* inb
     if ((double)sn[i].h > 0.1) excess = fabsf(diff) - sn[i].d * P->maxdiff * (float)P->lodsize;
     else excess = fabsf(diff);
     if (excess <= 0) continue;
-    const float transfer = P->settling * excess / 2.0f;
+    const float transfer = (P->settling * damp) * excess / 2.0f; /* damp: 1, or 2^-n in a crowd (see cur_damp) */
     const int32_t t = orc_ls_quantize_height(transfer);
     if (diff > 0) { B[4] -= t; D[4] -= t; B[sn[i].k] += t; D[sn[i].k] += t; }
     else { B[4] += t; D[4] += t; B[sn[i].k] -= t; D[sn[i].k] -= t; }
@@ -545,7 +545,7 @@ static int ls_step(orc_ls_world* w, const int32_t* R, orc_drop* d, int32_t* D, i
     }
   st->steps++;
   if (d->flags & ORC_DROP_CASCADE) { /* water.h:151 of the previous call */
-    st->cascade_transfers += ls_cascade_block(P, B, inb, D);
+    st->cascade_transfers += ls_cascade_block(P, B, inb, D, w->cur_damp);
     d->flags &= ~ORC_DROP_CASCADE;
   }
   /* cellpool.h:181-204 on the block; height() of a missing cell is 0 (cellpool.h:433-437) */
@@ -581,7 +581,7 @@ static int ls_step(orc_ls_world* w, const int32_t* R, orc_drop* d, int32_t* D, i
   }
   float effD = P->depositionRate * (1.0f - root); /* :86-87 */
   if (effD < 0) effD = 0;
-  effD = effD * w->cur_damp; /* 1, or 0.5 next to a drop with a higher key (exclusive_cells == 3) */
+  effD = effD * w->cur_damp; /* 1, or 2^-n next to n cells holding a higher key (exclusive_cells == 3) */
   {
     const float g = lod * P->gravity; /* :95 */
     d->sx += (g * nx) / d->volume;
@@ -679,12 +679,12 @@ void orc_ls_run(orc_ls_world* w, orc_drop* drops, size_t n, orc_stats* st, float
         w->cur_damp = 1.0f;
         if (!blocked && w->exclusive_cells >= 2) { /* a drop with a higher key stands on one of the 8 cells around */
           const int x = trunc_i(drops[i].px), y = trunc_i(drops[i].py);
-          int crowded = 0;
+          int crowded = 0; /* cells around that hold a higher key */
           for (int dx = -1; dx <= 1; dx++)
             for (int dy = -1; dy <= 1; dy++)
-              if ((dx || dy) && !ls_oob(w, x + dx, y + dy) && claim[(size_t)(x + dx) * size + (y + dy)] > key) crowded = 1;
-          if (crowded && w->exclusive_cells == 2) blocked = 1;     /* 2: wait */
-          else if (crowded) w->cur_damp = 0.5f;                     /* 3: step, with half the sediment exchange */
+              if ((dx || dy) && !ls_oob(w, x + dx, y + dy) && claim[(size_t)(x + dx) * size + (y + dy)] > key) crowded++;
+          if (crowded && w->exclusive_cells == 2) blocked = 1;       /* 2: wait */
+          else if (crowded) w->cur_damp = ldexpf(1.0f, -crowded);   /* 3: step, the sediment exchange halved per such cell */
         }
         if (blocked) {
           const int waited = (drops[i].flags >> ORC_DROP_WAITED_SHIFT) & 7;

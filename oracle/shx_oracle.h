@@ -128,7 +128,7 @@ typedef struct {
   int exclusive_cells; /* 1: of the drops that stand on the same cell in a phase only the holder of the highest
                           claim key steps, the others wait for the next phase; 2: a drop also waits while a
                           higher key stands on one of the eight cells around it; 3 (default): such a drop steps,
-                          but with half the sediment exchange; 0: no turn-taking */
+                          with its sediment exchange halved per such cell; 0: no turn-taking */
   float cur_damp;      /* internal: factor on the sediment exchange of the step being made */
   int steps_per_phase; /* S >= 1 steps between two global meetings; within a phase a drop reads the frozen
                           plane plus its OWN earlier deltas of the phase (0 is read as 1) */

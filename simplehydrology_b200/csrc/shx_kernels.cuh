@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
     int v[9];
     float4 fld = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     unsigned held = 0u;
-    bool blocked = false;  // a drop with a higher key stands on one of the eight cells around
+    int crowded = 0;  // how many of the eight cells around hold a higher key this phase
     if (kCoop) {
       // 8 groups of 4 drops; lane (sub, k) loads neighbour cell k of drop 4g+sub of this warp -- its height
       // and its claim word of this phase, one 8-byte load -- the height into that drop's s_B row; a
@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
           s_Bw[src * 9 + co_k] = got[g].x;
           const unsigned key_src = __shfl_sync(0xffffffffu, mykey, src);
           const unsigned bal = __ballot_sync(0xffffffffu, (unsigned)got[g].y > key_src);
-          if ((lane >> 2) == g) blocked = ((bal >> (8 * (lane & 3))) & 0xFFu) != 0u;
+          if ((lane >> 2) == g) crowded = __popc((bal >> (8 * (lane & 3))) & 0xFFu);
         }
       }
     } else if (alive) {
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
       for (int k = 0; k < 9; k++) {
         const int off = (k / 3 - 1) * size + (k % 3 - 1);
         v[k] = ((inb >> k) & 1u) ? __ldcg(c + 4 * off) : 0;
-        if (k != 4 && ((inb >> k) & 1u)) blocked |= (unsigned)__ldcg(c + 4 * off + 1) > mykey;
+        if (k != 4 && ((inb >> k) & 1u)) crowded += (unsigned)__ldcg(c + 4 * off + 1) > mykey ? 1 : 0;
       }
       fld = __ldg(reinterpret_cast<const float4*>(a.m.rec + cidx));
       held = __ldcg(claim_at(ix, iy) + rw);
@@ -506,6 +506,9 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
       claim_max(claim_at((int)d.px, (int)d.py) + ww, claim_key(a.claim_epoch, phase + 2u, d), (int)d.px);
 
     if (turn) {
+      // 1, or 2^-n next to n cells that hold a higher key: what this drop moves (cascade transfers and the
+      // sediment exchange) is scaled down, so that the changes of neighbouring cells in one phase do not add up
+      const float damp = __int_as_float((127 - crowded) << 23);
       steps++;
       d.flags &= ~(7 << kWaitedShift);
 #pragma unroll
@@ -563,7 +566,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
               const float lim = above_tenth(hn) ? (diag ? a.P.lim_diag : a.P.lim_axis) : 0.0f;
               const float excess = fabsf(diff) - lim;
               if (diff != 0.0f && excess > 0.0f) {
-                const int t = h_quantize(a.P.settling * excess / 2.0f);  // world.h:154
+                const int t = h_quantize((a.P.settling * damp) * excess / 2.0f);  // world.h:154
                 const int s = diff > 0.0f ? t : -t;                       // world.h:157-164
                 Bc -= s;
                 const int k = (int)(j + (j >> 2));
@@ -617,9 +620,9 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
         }
         const float h2 = mv.oob ? oob_h2(hc) : h_to_float(hv);  // water.h:121-124
         float carried;
-        // next to a drop with a higher key the exchange is halved: neighbouring cells that change in the same
-        // phase form an explicit scheme whose factor (up to 1.1 per cell) must stay below 1 in sum
-        const float dh = exchange_math(hc, h2, cap, blocked ? mv.effD * 0.5f : mv.effD, d, a.P, carried);  // water.h:127-136
+        // The exchange is halved for every cell around that holds a higher key: neighbouring cells that change
+        // in the same phase form an explicit scheme whose factors (up to 1.1 per cell) must not add up.
+        const float dh = exchange_math(hc, h2, cap, mv.effD * damp, d, a.P, carried);  // water.h:127-136
         const int q = h_quantize(dh);
         dC += q;
         fx_eroded -= (long long)q;
