@@ -330,12 +330,17 @@ def run_cuda(args):
 
     # ---- e2e: the calls the host adaptor makes, with host buffers; with strips every rank downloads
     # its own rows into its own (whole-map sized, as the reference's) pool
-    pool = np.zeros(cells, shx.CELL_DTYPE)
-    shx.lib().shx_host_register(pool.ctypes.data, pool.nbytes)
+    # pinned host memory (cudaHostAlloc through torch; registering a pageable numpy buffer can fail silently under a
+    # low RLIMIT_MEMLOCK, which turns the 2-GiB download into a pageable copy at a quarter of the speed)
+    pool_t = torch.empty(cells * shx.CELL_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
+    pool_t.zero_()
+    pool = pool_t.numpy().view(shx.CELL_DTYPE)
     nroot = 4096
     rng = np.random.default_rng(5)
-    rxy = np.stack([rng.integers(strip.row0, strip.row1, nroot), rng.integers(0, 512 * MAPSIZE, nroot)], 1).astype(np.int32)
-    rval = np.zeros(nroot, np.float32)
+    rxy_t = torch.empty((nroot, 2), dtype=torch.int32, pin_memory=True)  # this step's inputs, pinned as well
+    rval_t = torch.zeros(nroot, dtype=torch.float32, pin_memory=True)
+    rxy, rval = rxy_t.numpy(), rval_t.numpy()
+    rxy[:] = np.stack([rng.integers(strip.row0, strip.row1, nroot), rng.integers(0, 512 * MAPSIZE, nroot)], 1)
     mask = shx.F_ALL if args.e2e_mask == "all" else (shx.F_HEIGHT | shx.F_DISCHARGE | shx.F_MOMENTUM)
     rec_bytes = 32 if args.e2e_mask == "all" else 16
     own_cells = (strip.row1 - strip.row0) * 512 * MAPSIZE
@@ -360,8 +365,7 @@ def run_cuda(args):
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(tsum)
-    shx.lib().shx_host_unregister(pool.ctypes.data)
-    del pool
+    del pool, pool_t
 
     # ---- the same loop when the per-frame consumers run on the device: no pool download; the vertex records go
     # into a device buffer (the renderer's VBO through interop) and the host reads back only the cells its
