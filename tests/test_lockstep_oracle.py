@@ -134,7 +134,7 @@ def test_drops_on_one_cell_take_turns(init_cells):
     assert st.phases == s1.phases == 502               # waiting does not prolong the call
     assert (k - 1) * 100 < st.steps <= k * s1.steps - (k - 1)  # every drop went its way, minus the steps spent waiting
     assert st.term_age + st.term_vol + st.term_oob == k
-    # without the exclusion all k step together in phase 0: fewer phases, a k-fold hit on the first cell
+    # without turn-taking all k step together in phase 0: no step is lost, but the first cell takes a k-fold hit
     free = orc.Ls(p)
     free.upload(init_cells)
     free.w.contents.exclusive_cells = 0
@@ -146,7 +146,7 @@ def test_drops_on_one_cell_take_turns(init_cells):
     assert abs(free.height_q(0)[c0] * H_LSB - h0) > abs(ls.height_q(0)[c0] * H_LSB - h0) * 0.99  # no smaller hit
 
 
-def test_exclusion_keeps_order_independence(init_cells):
+def test_turn_taking_keeps_order_independence(init_cells):
     p = orc.default_params(1)
     rng = np.random.default_rng(8)
     xy = np.repeat(rng.integers(100, 400, size=(40, 2)).astype(np.float32), 6, axis=0)  # six drops per cell
@@ -158,3 +158,29 @@ def test_exclusion_keeps_order_independence(init_cells):
         st = ls.erode_spawnlist(xy[perm])
         out.append((ls.height_q(0).copy(), st.as_dict()))
     assert np.array_equal(out[0][0], out[1][0]) and out[0][1] == out[1][1]
+
+
+def test_crowd_damping_only_acts_next_to_a_higher_key(init_cells):
+    """Two drops on NEIGHBOURING cells both step (no waiting), and the one with the lower key moves half as much in
+    that phase; far apart, both behave like a lone drop."""
+    p = orc.default_params(1)
+
+    def first_step_delta(xy):
+        ls = orc.Ls(p)
+        ls.upload(init_cells)
+        before = ls.height_q(0).copy()
+        drops, _ = ls.make_drops(np.asarray(xy, np.float32))
+        drops["age"] = 500  # one real step each: with age 501 > maxAge the next call ends the drop (water.h:74)
+        st, _ = ls.run_drops(drops)
+        return ls.height_q(0).astype(np.int64) - before, st
+
+    lone_a, _ = first_step_delta([[200.5, 200.5]])
+    lone_b, _ = first_step_delta([[200.5, 201.5]])
+    far, st_far = first_step_delta([[200.5, 200.5], [300.5, 300.5]])
+    assert st_far.steps == 4                           # one descend call each, plus the terminating one
+    assert np.array_equal(far[190:210, 190:210], lone_a[190:210, 190:210])  # a distant drop changes nothing here
+    near, st_near = first_step_delta([[200.5, 200.5], [200.5, 201.5]])
+    assert st_near.steps == st_far.steps               # neighbours do not wait for each other
+    both = lone_a + lone_b
+    assert not np.array_equal(near, both)              # ... but one of them was damped
+    assert np.abs(near).sum() < np.abs(both).sum()
