@@ -2,8 +2,8 @@
 // index i = (x - xlo)*size + y (x-major like the reference, math.h:11-14, but one global plane
 // instead of 512^2 tiles):
 //   hq   int4 per cell: the two Q5.26 height planes and the two claim words {plane0, claim0, plane1, claim1}.  A phase reads
-//        plane p&1 and adds into plane (p+1)&1 (see descend_lockstep); interleaving puts both in
-//        the same 32-byte sector, so the adds hit sectors the phase has just read.
+//        plane p&1 and adds into plane (p+1)&1 (see descend_lockstep); interleaving puts all four in
+//        the same 32-byte sector, so the adds and claims hit sectors the phase has just read.
 //   rec  32-byte record per cell = one L2 sector:
 //        {discharge, momentumx, momentumy, rootdensity}  fp32, read-only inside erode
 //        {track_d, track_mx, track_my, pad}              int32 Q13.18 accumulators (RED targets)
@@ -241,14 +241,20 @@ __device__ __forceinline__ float ord2f(unsigned u) {
 }
 
 
-// Same-cell exclusion.  A phase reads frozen heights, so two drops standing on one cell would both
-// erode it by the full amount -- over-erosion that feeds on itself in busy river cells (a 2048^2 map
-// ran away within 25 calls without this).  Of the drops on one cell only the holder of the highest
-// key steps in a phase; the others wait.  Keys are claimed one phase ahead with atomicMax on the
-// cell's claim word of the NEXT phase's parity.  The two claim words sit next to the two height words
-// of the cell (one 16-byte int4 per cell): the word a drop claims belongs to a sector its gather has
-// just pulled into L2, and the word it checks arrives with its centre height.  (In a plane of their
-// own the claims cost +3.3 ms per 8192^2 cycle: every claim was a DRAM read-modify-write.)
+// Turn-taking and crowd damping.  A phase reads frozen heights, so two drops standing on one cell would
+// both erode it by the full amount, and drops on neighbouring cells (a train along a river) change
+// coupled cells at once -- an explicit scheme whose per-cell factors add up.  Left alone this runs
+// away (a 2048^2 map within 25 calls, 8192^2 with same-cell turn-taking only after ~100).  Two rules:
+//  * of the drops on one cell only the holder of the highest key steps in a phase; the others wait,
+//    and a phase spent waiting is a step of the drop's life not taken (bounded phases per launch);
+//  * what a stepping drop moves (cascade transfers, sediment exchange) is halved for every one of the
+//    eight cells around it that holds a higher key in this phase.
+// Keys are claimed one phase ahead with atomicMax on the cell's claim word of the NEXT phase's parity.
+// The claim words sit next to the height words of the cell (one 16-byte int4 {h0, claim0, h1, claim1}):
+// the word a drop claims belongs to a sector its gather has just pulled into L2, the word it checks
+// arrives with its centre height, and the neighbours' claims ride on the cooperative gather's 8-byte
+// loads.  (In a plane of their own the claims cost +3.3 ms per 8192^2 cycle: every claim was a DRAM
+// read-modify-write.)
 //   key = {launch epoch : 4 | phase tag : 12 | phases waited so far, saturating : 3 | state hash : 13}
 // i.e. longest waiting first, then an order-independent pseudo-random choice; equal keys all step.
 // The epoch makes the keys of earlier launches lose; the host clears the words when it wraps.
