@@ -184,3 +184,31 @@ def test_crowd_damping_only_acts_next_to_a_higher_key(init_cells):
     both = lone_a + lone_b
     assert not np.array_equal(near, both)              # ... but one of them was damped
     assert np.abs(near).sum() < np.abs(both).sum()
+
+
+def test_schedule_is_as_close_to_the_reference_as_a_reorder(init_cells):
+    """North-star check 3 on the CPU: after 10 erode(512) cycles on the reference's default world the lock-step
+    schedule (turn-taking, crowd damping, fixed point) differs from the sequential reference semantics by about as
+    much as those differ from themselves with the drops of each cycle processed in another order."""
+    def metrics(a, b):
+        da = a["height"].astype(np.float64) - init_cells["height"]
+        db = b["height"].astype(np.float64) - init_cells["height"]
+        return (float(np.sqrt(np.mean((da - db) ** 2))), float(np.corrcoef(da, db)[0, 1]),
+                float(np.corrcoef(a["discharge"], b["discharge"])[0, 1]))
+
+    rng = np.random.default_rng(7)
+    spawns = [rng.integers(0, 512, size=(512, 2)).astype(np.float32) for _ in range(10)]
+    ref, shuf = init_cells.copy(), init_cells.copy()
+    S, S2 = orc.Seq(ref), orc.Seq(shuf)
+    ls = orc.Ls(orc.default_params(1))
+    ls.upload(init_cells)
+    for c, xy in enumerate(spawns):
+        S.erode_spawnlist(xy)
+        S2.erode_spawnlist(xy[np.random.default_rng(1000 + c).permutation(512)])
+        ls.erode_spawnlist(xy)
+    got = ls.download()
+    rmse_b, corr_b, cdis_b = metrics(ref, shuf)
+    rmse_l, corr_l, cdis_l = metrics(ref, got)
+    assert rmse_l <= 1.25 * rmse_b and corr_l >= corr_b - 0.03 and cdis_l >= cdis_b - 0.05
+    total = got["discharge"].sum(dtype=np.float64) / ref["discharge"].sum(dtype=np.float64)
+    assert abs(total - 1.0) < 0.02  # waiting costs the drops next to no steps at the reference's own density
