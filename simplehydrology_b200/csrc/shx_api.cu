@@ -582,7 +582,7 @@ static int fetch_stats(shx_ctx* c, shx_stats* out) {
   if (c->h_flags[2]) {
     const int why = c->h_flags[2];
     CU(cudaMemsetAsync(c->d_flags + 2, 0, sizeof(int), c->stream));
-    if (why == 2) return fail(SHX_ERR_RANGE, "a launch needed more than 16000 phases (drops queueing for one cell); the call's result is invalid");
+    if (why == 2) return fail(SHX_ERR_RANGE, "a launch needed more than 4000 phases (the batched mode supports maxAge up to ~3990); the call's result is invalid");
     return fail(SHX_ERR_PEER, "a peer GPU did not reach a phase barrier within the time-out; the call's result is invalid");
   }
   if (c->h_flags[0]) {
