@@ -656,6 +656,7 @@ void orc_ls_run(orc_ls_world* w, orc_drop* drops, size_t n, orc_stats* st, float
   memset(&local, 0, sizeof(local));
   /* exclusive_cells: claim[c] = highest key {phase tag, phases waited, state hash} of the awake drops on cell c */
   uint32_t* claim = w->exclusive_cells ? (uint32_t*)calloc((size_t)size * size, sizeof(uint32_t)) : NULL;
+  unsigned char* freew = w->free_waits > 0 ? (unsigned char*)calloc(n ? n : 1, 1) : NULL;
   for (uint64_t phase = 0;; phase++) {
     const int32_t* R = w->h[phase & 1];
     size_t active = 0;
@@ -692,6 +693,10 @@ void orc_ls_run(orc_ls_world* w, orc_drop* drops, size_t n, orc_stats* st, float
           /* A phase spent waiting is a step of the drop's life not taken: the age advances, so a call never needs
            * more phases than maxAge + 2 however long the queues.  A drop that expires in the queue leaves its
            * sediment where it stands (water.h:74-77). */
+          if (freew && freew[i] < w->free_waits) { /* design study (orc_ls_world.free_waits): this wait does not cost a step */
+            freew[i]++;
+            continue;
+          }
           drops[i].age++;
           if ((float)drops[i].age > w->p.maxAge) {
             int32_t* D = deltas + 9 * (i * S);
@@ -747,7 +752,7 @@ void orc_ls_run(orc_ls_world* w, orc_drop* drops, size_t n, orc_stats* st, float
     st->fx_eroded += local.fx_eroded; st->fx_deposited += local.fx_deposited;
     st->fx_sed_oob_lost += local.fx_sed_oob_lost; st->fx_sed_deposited += local.fx_sed_deposited; st->fx_sed_inflation += local.fx_sed_inflation;
   }
-  free(deltas); free(dpos); free(has); free(claim);
+  free(deltas); free(dpos); free(has); free(claim); free(freew);
 }
 
 void orc_ls_reset_tracks(orc_ls_world* w) { /* world.h:56-61 */

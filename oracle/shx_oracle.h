@@ -130,6 +130,7 @@ typedef struct {
                           higher key stands on one of the eight cells around it; 3 (default): such a drop steps,
                           with its sediment exchange halved per such cell; 0: no turn-taking */
   float cur_damp;      /* internal: factor on the sediment exchange of the step being made */
+  int free_waits;      /* design study, 0 in the product: this many waits per drop and run do not advance its age */
   int steps_per_phase; /* S >= 1 steps between two global meetings; within a phase a drop reads the frozen
                           plane plus its OWN earlier deltas of the phase (0 is read as 1) */
 } orc_ls_world;
