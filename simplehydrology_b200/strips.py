@@ -1,24 +1,23 @@
 """Row-strip decomposition of one world over the GPUs of a box: one process per GPU, one strip of
 rows (constant x, whole tiles) per rank, neighbour-only exchange through torch.distributed.
 
-Per World::erode call (world.h:54-88) every rank
-  1. resets its tracks, spawns the drops of ITS nodes and marches them in lock step until they
-     finish or leave the strip (shx_strip_erode_begin);
-  2. exchange round, repeated until no drop is in flight anywhere:
-       a. the integer height deltas a strip accumulated in its halo rows (cascade transfers across
-          the strip border) go to the owner, which adds them to its edge rows;
-       b. the owners' fresh edge rows come back and refresh the halos;
-       c. drops that left a strip (28-byte Drop record + status word) go to the neighbour, which
-          marches them on (shx_strip_run_device_drops);
-  3. runs the EMA over its own rows (shx_strip_erode_end).
-Only neighbours talk (send/recv); the single collective is the 1-int "anything still in flight?"
-all-reduce.  Everything exchanged is an integer or a bit-copied record, so a k-strip run is
-deterministic for given k.  It is NOT bit-identical to the 1-GPU run: a drop that crosses a border
-pauses until the round ends, i.e. the lock-step schedule differs near borders.  Parity with the
-single-domain result is statistical (tests/test_gpu_strips.py).
+Three protocols, all deterministic for a given number of strips:
 
-The exchange logic is backend-agnostic: `GpuStrip` drives libshx on a CUDA device; tests drive the
-same StripExchange with a CPU stand-in over gloo (tests/test_strips_gloo.py).
+  StripExchange.erode_cycle   ONE exchange per World::erode call (the default of bench.py --gpus N):
+      every rank resets its tracks, spawns the drops of ITS nodes, appends the drops its neighbours
+      handed over at the end of the previous call (they sleep until the phase equal to their age) and
+      marches them in lock step until they finish or leave the strip; runs the EMA over its own
+      rows; then one message per neighbour carries the migrant records, the integer height deltas
+      accumulated in the halo rows and the current edge rows.  No collective, no host sync.
+  StripExchange.erode         exchange ROUNDS within the call until no drop is in flight anywhere
+      (halo deltas -> owner, edge rows -> halos, migrants -> neighbour, one 1-int all-reduce).
+  PeerWorld                   no exchange by the host at all: the strips are mapped into each other
+      (CUDA IPC) and the descend kernel crosses NVLink itself; bit-identical to one GPU.
+
+The first two are statistically, not bitwise, the single-domain result (a crossing drop pauses,
+halos are stale for a round / a call); tests/test_gpu_strips.py and tests/test_gpu_reference_parity.py
+state the bounds.  The exchange logic is backend-agnostic: `GpuStrip` drives libshx on a CUDA
+device; tests drive the same StripExchange with a CPU stand-in over gloo (tests/test_strips_gloo.py).
 """
 import numpy as np
 import torch
