@@ -61,8 +61,13 @@ def lib():
     if _lib is None:
         path = os.path.join(ORACLE_DIR, "libshx_oracle.so")
         srcs = [os.path.join(ORACLE_DIR, f) for f in ("shx_oracle.c", "shx_oracle.h")]
-        if not os.path.exists(path) or any(os.path.getmtime(f) > os.path.getmtime(path) for f in srcs):
-            build_oracle()  # make only rebuilds what is out of date
+        if not os.path.exists(path):
+            build_oracle()
+        elif any(os.path.getmtime(f) > os.path.getmtime(path) for f in srcs):
+            try:
+                build_oracle()  # make only rebuilds what is out of date
+            except Exception:   # e.g. a snapshot that did not keep time stamps on a box without a compiler
+                pass
         L = C.CDLL(path)
         L.orc_tiled_index.restype = C.c_size_t
         L.orc_tiled_index.argtypes = [C.POINTER(Params), C.c_int, C.c_int]
