@@ -129,9 +129,10 @@ typedef struct {
   int peer_rank, peer_world;
   /* batched mode: at most this many drops per node march together; a call with more cycles runs as
    * consecutive batches (reset once before, EMA once after).  All drops of a batch read the same
-   * frozen heights each step, so the batch must stay sparse: 512 per 512^2 node per batch is what
-   * the reference's frame loop issues (SimpleHydrology.cpp:319); much denser batches over-erode
-   * cells several drops share and can run away.  0 = 512. */
+   * frozen heights each step and take turns on shared cells (a waiting phase costs the drop a step
+   * of its life), so a batch should stay sparse: 512 per 512^2 node per batch is what the
+   * reference's frame loop issues (SimpleHydrology.cpp:319); in much denser batches the drops
+   * spend their lives queueing.  0 = 512. */
   int max_cycles_per_launch;
 } shx_config;
 
