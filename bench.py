@@ -441,7 +441,7 @@ def run_cuda(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)  # 40 cycles ~ 0.5 s timed: several clock samples
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--e2e-mask", default="all", choices=["all", "hdm"])
