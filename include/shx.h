@@ -78,7 +78,10 @@ enum {
   SHX_DROP_DONE_NULL = 64,   /* water.h:62-68 */
   SHX_DROP_MIGRATE_LO = 128, /* left this strip towards smaller x */
   SHX_DROP_MIGRATE_HI = 256,
-  SHX_DROP_WAITED_SHIFT = 16 /* bits 16-18: phases the drop has been waiting for its cell (batched mode, saturating at 7) */
+  SHX_DROP_WAITED_SHIFT = 16, /* bits 16-18: phases the drop has been waiting for its cell (batched mode, saturating at 7);
+                                 the k-th of several drops created on the same position starts with min(k, 7) */
+  SHX_DROP_FREEW_SHIFT = 19,  /* bits 19-22: waits of this drop that did not cost it a step (<= shx_config.free_waits) */
+  SHX_DROP_CHECK_SPAWN = 1 << 24 /* sequential mode: apply the height < 0.1 rejection when the drop starts (world.h:71-72) */
 };
 
 /* Counters of one call.  fx_* are exact integers: heights in Q5.26 (2^-26 units),
@@ -115,7 +118,9 @@ typedef struct {
    * Results never depend on them: every shape is bit-identical. */
   int block_threads;   /* CTA size */
   int grid_blocks;     /* cap on the grid (smaller than the drop count => several launches in list order) */
-  int variant;         /* register budget: 0 = 64 (1024 threads/SM), 1 = 128 (512/SM), 2 = 72 (7x128/SM), 3 = 72 (2x448/SM) */
+  int variant;         /* one thread per drop, register budget: 0 = 64 (1024 threads/SM), 1 = 128 (512/SM), 2 = 72 (7x128/SM),
+                          3 = 72 (2x448/SM); 5 = eight lanes per drop (what the library picks for batches of up to
+                          ~19 000 drops) in CTAs of block_threads */
   int keep_tracks;     /* 0: erode's EMA pass also zeroes the *_track accumulators (the reset the reference
                           does at the START of the next call, world.h:56-61, hoisted into the same pass);
                           1: leave them readable after erode, at the cost of one more pass per call */
@@ -134,6 +139,11 @@ typedef struct {
    * reference's frame loop issues (SimpleHydrology.cpp:319); in much denser batches the drops
    * spend their lives queueing.  0 = 512. */
   int max_cycles_per_launch;
+  /* batched mode: the first free_waits (0..15; shx_default_config sets 8) phases a drop spends waiting for its cell do
+   * not cost it a step of its life; every later wait does (the reference's drops never wait: without the budget the
+   * queues in river cells cost the drops ~3 % of their steps, with 8 free waits ~1 %).  A launch needs at most
+   * maxAge + 2 + free_waits phases. */
+  int free_waits;
 } shx_config;
 
 /* CUDA IPC handles of one rank's strip (opaque bytes; gather them from all ranks with the caller's

@@ -379,6 +379,8 @@ orc_ls_world* orc_ls_create(const orc_params* p) {
   w->row1 = w->size;
   w->exclusive_cells = 3;
   w->cur_damp = 1.0f;
+  w->free_waits = 8;  /* shx_config.free_waits default */
+  w->recip_evap = 1;  /* the batched kernels multiply by 1/(1-evapRate) instead of dividing */
   return w;
 }
 
@@ -445,6 +447,19 @@ void orc_ls_spawn(const orc_params* p, uint64_t seed, uint64_t epoch, int cycles
 
 static int ls_oob(const orc_ls_world* w, int x, int y) { return x < 0 || y < 0 || x >= w->size || y >= w->size; }
 
+/* Twins: drops created on bit-identical positions in one batch have identical state, hence identical claim keys,
+ * and would step together for their whole lives (each applying the full erosion to the same cells).  The k-th
+ * duplicate of a position starts with `waited` = min(k, 7): the copies take their first turns one after another and
+ * are different drops from then on.  Which copy gets which rank does not matter (they are identical), so the result
+ * stays independent of the order of the list. */
+typedef struct { uint32_t x, y; size_t i; } twin_key;
+static int twin_cmp(const void* a, const void* b) {
+  const twin_key* p = (const twin_key*)a; const twin_key* q = (const twin_key*)b;
+  if (p->x != q->x) return p->x < q->x ? -1 : 1;
+  if (p->y != q->y) return p->y < q->y ? -1 : 1;
+  return p->i < q->i ? -1 : (p->i > q->i);
+}
+
 void orc_ls_make_drops(const orc_ls_world* w, const float* xy, size_t n, orc_drop* drops, orc_stats* st) {
   for (size_t i = 0; i < n; i++) {
     orc_drop d = {xy[2 * i], xy[2 * i + 1], 0.0f, 0.0f, 1.0f, 0.0f, 0, ORC_DROP_ALIVE};
@@ -454,6 +469,21 @@ void orc_ls_make_drops(const orc_ls_world* w, const float* xy, size_t n, orc_dro
     else if (ls_oob(w, ix, iy)) { d.flags = ORC_DROP_DONE_NULL; }
     else if (st) st->spawned++;
     drops[i] = d;
+  }
+  if (n > 1) {
+    twin_key* k = (twin_key*)malloc(sizeof(twin_key) * n);
+    for (size_t i = 0; i < n; i++) { memcpy(&k[i].x, &xy[2 * i], 4); memcpy(&k[i].y, &xy[2 * i + 1], 4); k[i].i = i; }
+    qsort(k, n, sizeof(twin_key), twin_cmp);
+    for (size_t a = 0; a < n;) {
+      size_t b = a + 1;
+      while (b < n && k[b].x == k[a].x && k[b].y == k[a].y) b++;
+      for (size_t r = a + 1; r < b; r++) {
+        const int rank = (int)(r - a) < 7 ? (int)(r - a) : 7;
+        if (drops[k[r].i].flags & ORC_DROP_ALIVE) drops[k[r].i].flags |= rank << ORC_DROP_WAITED_SHIFT;
+      }
+      a = b;
+    }
+    free(k);
   }
 }
 
@@ -628,7 +658,8 @@ static int ls_step(orc_ls_world* w, const int32_t* R, orc_drop* d, int32_t* D, i
     st->fx_eroded -= q;
   }
   const float carried = d->sediment;
-  d->sediment = (float)((double)d->sediment / (1.0 - (double)P->evapRate)); /* :135 */
+  if (w->recip_evap) d->sediment = (float)((double)d->sediment * (1.0 / (1.0 - (double)P->evapRate))); /* :135 as a multiplication */
+  else d->sediment = (float)((double)d->sediment / (1.0 - (double)P->evapRate)); /* :135 */
   d->volume = (float)((double)d->volume * (1.0 - (double)P->evapRate));     /* :136 */
   st->fx_sed_inflation += tq(d->sediment) - tq(carried);
   if (out) { /* :139-142 */
@@ -656,7 +687,6 @@ void orc_ls_run(orc_ls_world* w, orc_drop* drops, size_t n, orc_stats* st, float
   memset(&local, 0, sizeof(local));
   /* exclusive_cells: claim[c] = highest key {phase tag, phases waited, state hash} of the awake drops on cell c */
   uint32_t* claim = w->exclusive_cells ? (uint32_t*)calloc((size_t)size * size, sizeof(uint32_t)) : NULL;
-  unsigned char* freew = w->free_waits > 0 ? (unsigned char*)calloc(n ? n : 1, 1) : NULL;
   for (uint64_t phase = 0;; phase++) {
     const int32_t* R = w->h[phase & 1];
     size_t active = 0;
@@ -693,9 +723,12 @@ void orc_ls_run(orc_ls_world* w, orc_drop* drops, size_t n, orc_stats* st, float
           /* A phase spent waiting is a step of the drop's life not taken: the age advances, so a call never needs
            * more phases than maxAge + 2 however long the queues.  A drop that expires in the queue leaves its
            * sediment where it stands (water.h:74-77). */
-          if (freew && freew[i] < w->free_waits) { /* design study (orc_ls_world.free_waits): this wait does not cost a step */
-            freew[i]++;
-            continue;
+          { /* the first free_waits waits of a drop's life do not cost it a step (counter in the flag word) */
+            const int fw = (drops[i].flags >> ORC_DROP_FREEW_SHIFT) & 15;
+            if (fw < w->free_waits) {
+              drops[i].flags = (drops[i].flags & ~(15 << ORC_DROP_FREEW_SHIFT)) | ((fw + 1) << ORC_DROP_FREEW_SHIFT);
+              continue;
+            }
           }
           drops[i].age++;
           if ((float)drops[i].age > w->p.maxAge) {
@@ -752,7 +785,7 @@ void orc_ls_run(orc_ls_world* w, orc_drop* drops, size_t n, orc_stats* st, float
     st->fx_eroded += local.fx_eroded; st->fx_deposited += local.fx_deposited;
     st->fx_sed_oob_lost += local.fx_sed_oob_lost; st->fx_sed_deposited += local.fx_sed_deposited; st->fx_sed_inflation += local.fx_sed_inflation;
   }
-  free(deltas); free(dpos); free(has); free(claim); free(freew);
+  free(deltas); free(dpos); free(has); free(claim);
 }
 
 void orc_ls_reset_tracks(orc_ls_world* w) { /* world.h:56-61 */

@@ -66,7 +66,8 @@ enum {
   ORC_DROP_DONE_NULL = 64,   /* water.h:62-68 (spawned outside the map) */
   ORC_DROP_MIGRATE_LO = 128, /* left the strip towards smaller x (multi-GPU hand-off) */
   ORC_DROP_MIGRATE_HI = 256,
-  ORC_DROP_WAITED_SHIFT = 16 /* bits 16-18: phases the drop has waited for its cell (lock-step exclusion), saturating at 7 */
+  ORC_DROP_WAITED_SHIFT = 16, /* bits 16-18: phases the drop has waited for its cell (lock-step exclusion), saturating at 7 */
+  ORC_DROP_FREEW_SHIFT = 19   /* bits 19-22: waits of this drop that did not cost it a step (at most free_waits <= 15) */
 };
 
 typedef struct {
@@ -130,7 +131,10 @@ typedef struct {
                           higher key stands on one of the eight cells around it; 3 (default): such a drop steps,
                           with its sediment exchange halved per such cell; 0: no turn-taking */
   float cur_damp;      /* internal: factor on the sediment exchange of the step being made */
-  int free_waits;      /* design study, 0 in the product: this many waits per drop and run do not advance its age */
+  int free_waits;      /* the first free_waits (<= 15, default 8 = shx_config.free_waits) waits of a drop's life do not
+                          advance its age; later ones cost a step each, which bounds the phases of a call */
+  int recip_evap;      /* 1 (default): water.h:135 as a multiplication by the double 1/(1-evapRate), like the batched
+                          kernels; 0: the reference's division */
   int steps_per_phase; /* S >= 1 steps between two global meetings; within a phase a drop reads the frozen
                           plane plus its OWN earlier deltas of the phase (0 is read as 1) */
 } orc_ls_world;

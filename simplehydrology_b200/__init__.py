@@ -46,7 +46,7 @@ class Config(C.Structure):
     _fields_ = [("device", C.c_int), ("mode", C.c_int), ("row0", C.c_int), ("row1", C.c_int), ("halo", C.c_int),
                 ("max_drops", C.c_size_t), ("block_threads", C.c_int), ("grid_blocks", C.c_int), ("variant", C.c_int),
                 ("keep_tracks", C.c_int), ("coop", C.c_int), ("peer_rank", C.c_int), ("peer_world", C.c_int),
-                ("max_cycles_per_launch", C.c_int)]
+                ("max_cycles_per_launch", C.c_int), ("free_waits", C.c_int)]
 
 
 class PeerHandles(C.Structure):
@@ -155,7 +155,7 @@ class World:
 
     def __init__(self, params=None, mapsize=1, mode=MODE_BATCHED, device=0, row0=0, row1=0, halo=2, max_drops=0,
                  block_threads=0, grid_blocks=0, variant=0, keep_tracks=0, coop=0, peer_rank=0, peer_world=0,
-                 max_cycles_per_launch=0):
+                 max_cycles_per_launch=0, free_waits=None):
         self.L = lib()
         self.params = params if params is not None else default_params(mapsize)
         cfg = Config()
@@ -165,6 +165,8 @@ class World:
         cfg.keep_tracks, cfg.coop = keep_tracks, coop
         cfg.peer_rank, cfg.peer_world = peer_rank, peer_world
         cfg.max_cycles_per_launch = max_cycles_per_launch
+        if free_waits is not None:
+            cfg.free_waits = free_waits
         self.cfg = cfg
         self.size = self.params.mapsize * self.params.tilesize
         self.ncells = self.size * self.size

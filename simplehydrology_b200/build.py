@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libshx.so")
 SOURCES = [os.path.join(HERE, "csrc", "shx_api.cu")]
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("shx_api.cu", "shx_kernels.cuh", "shx_aux_kernels.cuh", "shx_view_kernels.cuh", "shx_step.cuh", "shx_math.cuh")] + \
+DEPS = sorted(os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc")) if f.endswith((".cu", ".cuh", ".h"))) + \
        [os.path.join(ROOT, "include", "shx.h")]
 
 NVCC_FLAGS = [

@@ -16,6 +16,9 @@ struct LaunchShape {
   const void* kernel = nullptr;
   int block = 0;
   int cap_blocks = 0;  // co-resident CTAs (cooperative launch limit)
+  bool group = false;  // descend_group_kernel (eight lanes per drop) rather than one thread per drop
+  size_t smem(int b) const;
+  size_t drops_per_block(int b) const { return group ? (size_t)b / 8 : (size_t)b; }
 };
 
 struct TimingSpan {
@@ -24,6 +27,9 @@ struct TimingSpan {
 };
 
 using namespace shx;
+
+// one thread per drop: s_B[9] + s_D[2][8] + s_S[8] x 2 words per thread; eight lanes per drop: 3 words per lane
+size_t LaunchShape::smem(int b) const { return (size_t)(group ? kGroupSmemWords : 41) * sizeof(int32_t) * b; }
 
 static thread_local std::string g_err;
 
@@ -94,6 +100,7 @@ static StepParams step_params(const shx_params& p) {
   s.lim_axis = 1.0f * p.maxdiff * (float)p.lodsize;
   s.lim_diag = sqrtf(2.0f) * p.maxdiff * (float)p.lodsize;
   s.keep = 1.0 - (double)p.evapRate;  // water.h:135-136
+  s.inv_keep = 1.0 / s.keep;
   return s;
 }
 
@@ -105,8 +112,6 @@ static int grid_for(const shx_ctx* c, size_t n, int block = 256) {
   return (int)std::max<size_t>(1, std::min(want, cap));
 }
 
-// s_B[9] + s_D[2][8] + s_S[8] x 2 words, per thread
-static size_t descend_smem(int block) { return (size_t)(9 + 16 + 16) * sizeof(int32_t) * block; }
 
 // Instantiations {max CTA threads, min CTAs/SM}.  KERNEL_SMALL: one CTA of up to 1024 threads for
 // small batches (the barrier is a plain __syncthreads).  Multi-CTA: the first four cap registers at
@@ -114,7 +119,7 @@ static size_t descend_smem(int block) { return (size_t)(9 + 16 + 16) * sizeof(in
 // 7 CTAs of 128 threads per SM = 896 threads at 72 registers, just enough for the 886 drops per SM
 // of an 8192^2 cycle.
 // The last template argument selects the warp-cooperative block gather (see shx_kernels.cuh).
-#define KERNEL_SMALL descend_lockstep_kernel<1024, 1, false>
+#define KERNEL_SMALL descend_group_kernel<1024, 1>
 #define PICK(T, B) (coop ? (const void*)descend_lockstep_kernel<T, B, true> : (const void*)descend_lockstep_kernel<T, B, false>)
 static const void* big_kernel(int block, int variant, bool coop) {
   if (variant == 2) return PICK(128, 7);
@@ -155,6 +160,7 @@ void shx_default_config(shx_config* c) {
   memset(c, 0, sizeof(*c));
   c->mode = SHX_MODE_BATCHED;
   c->halo = 2;
+  c->free_waits = 8;
 }
 
 void shx_destroy(shx_ctx* c) {
@@ -177,8 +183,8 @@ int shx_create(shx_ctx** out, const shx_params* p, const shx_config* cfg_in) {
   if (!out || !p) return fail(SHX_ERR_ARG, "shx_create: null argument");
   *out = nullptr;
   if (p->lodsize != 1) return fail(SHX_ERR_ARG, "only lodsize == 1 is supported (cellpool.h:178)");
-  if (p->mapsize < 1 || p->tilesize < 4 || (long long)p->mapsize * p->tilesize > 32768)
-    return fail(SHX_ERR_ARG, "bad geometry (side must be <= 32768 cells)");
+  if (p->mapsize < 1 || p->tilesize < 4 || (long long)p->mapsize * p->tilesize > 16384)
+    return fail(SHX_ERR_ARG, "bad geometry (side must be <= 16384 cells: cell indices travel in 28 bits)");
   shx_config cfg;
   if (cfg_in) cfg = *cfg_in; else shx_default_config(&cfg);
   const int size = p->mapsize * p->tilesize;
@@ -195,6 +201,7 @@ int shx_create(shx_ctx** out, const shx_params* p, const shx_config* cfg_in) {
   }
   if (cfg.row0 == 0 && cfg.row1 == 0) cfg.row1 = size;
   if (cfg.row0 < 0 || cfg.row1 > size || cfg.row0 >= cfg.row1) return fail(SHX_ERR_ARG, "bad strip rows");
+  if (cfg.free_waits < 0 || cfg.free_waits > 15) return fail(SHX_ERR_ARG, "free_waits must be 0..15");
   const bool whole = cfg.row0 == 0 && cfg.row1 == size;
   if (!whole && !peer && cfg.halo < 2) return fail(SHX_ERR_ARG, "strip halo must be >= 2 rows");
   if (!whole && cfg.mode == SHX_MODE_SEQUENTIAL) return fail(SHX_ERR_MODE, "sequential mode is whole-map only");
@@ -285,31 +292,43 @@ int shx_create(shx_ctx** out, const shx_params* p, const shx_config* cfg_in) {
     shx_destroy(c);
     return fail(SHX_ERR_ARG, "peer mode does not take launch-shape overrides");
   }
+  // shape[0] "group": eight lanes per drop in CTAs of 256 threads (32 drops), four CTAs per SM: batches of up to
+  // ~19 000 drops (latency regime: the reference's own sizes, the strips of a multi-GPU run); shape[1] "dense":
+  // one thread per drop, 2 x 448 threads per SM at 72 registers (throughput regime).  An explicit block_threads /
+  // variant / coop / grid_blocks in the config forces one shape for both (variant 5 = the group kernel).
   for (int i = 0; i < 2; i++) {
     LaunchShape& ls = c->shape[i];
-    if (forced) {
+    if (forced && cfg.variant == 5) {
+      ls.group = true;
+      ls.block = cfg.block_threads > 0 ? std::min(1024, (cfg.block_threads + 31) / 32 * 32) : 256;
+      ls.kernel = ls.block <= 256 ? (const void*)descend_group_kernel<256, 4> : (const void*)descend_group_kernel<1024, 1>;
+    } else if (forced) {  // one thread per drop in one of its shapes
       ls.block = cfg.block_threads > 0 ? std::min(1024, (cfg.block_threads + 31) / 32 * 32) : 256;
       if (cfg.variant == 1) ls.block = std::min(ls.block, 512);
       if (cfg.variant == 2) ls.block = std::min(ls.block, 128);
       if (cfg.variant == 3) ls.block = 448;
       ls.kernel = big_kernel(ls.block, cfg.variant, cfg.coop == 1);
+    } else if (i == 0 && !peer) {
+      ls.group = true;
+      ls.block = 256;
+      ls.kernel = (const void*)descend_group_kernel<256, 4>;
     } else if (i == 0) {
       ls.block = 64;
-      ls.kernel = peer ? (const void*)descend_lockstep_kernel<128, 7, true, true> : big_kernel(64, 2, true);
+      ls.kernel = (const void*)descend_lockstep_kernel<128, 7, true, true>;
     } else {
       ls.block = 448;
       ls.kernel = peer ? (const void*)descend_lockstep_kernel<448, 2, true, true> : big_kernel(448, 3, true);
     }
     int nb = 0;
-    if (cudaFuncSetAttribute(ls.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)descend_smem(ls.block)) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls.kernel, ls.block, descend_smem(ls.block)) != cudaSuccess || nb < 1) {
+    if (cudaFuncSetAttribute(ls.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls.smem(ls.block)) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ls.kernel, ls.block, ls.smem(ls.block)) != cudaSuccess || nb < 1) {
       shx_destroy(c);
       return fail(SHX_ERR_CUDA, "descend kernel does not fit on this device");
     }
     ls.cap_blocks = nb * c->sm_count;
   }
   c->forced_shape = forced;
-  if (cudaFuncSetAttribute(KERNEL_SMALL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)descend_smem(1024)) != cudaSuccess) {
+  if (cudaFuncSetAttribute(KERNEL_SMALL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kGroupSmemWords * 4 * 1024)) != cudaSuccess) {
     shx_destroy(c);
     return fail(SHX_ERR_CUDA, "descend kernel does not fit on this device");
   }
@@ -660,6 +679,8 @@ static int run_device_drops(shx_ctx* c, size_t n, bool trace, bool align_age = f
     a.drops = c->d_drops;
     a.ndrops = (unsigned)n;
     a.align_age = 0u;
+    a.free_waits = (unsigned)c->cfg.free_waits;
+    a.abort_flag = c->d_flags + 2;  // OR-ed by the kernels, cleared when the stats are read
     a.bar = c->d_bar;
     a.stats = c->d_stats;
     a.trace = trace ? c->d_trace : nullptr;
@@ -669,14 +690,12 @@ static int run_device_drops(shx_ctx* c, size_t n, bool trace, bool align_age = f
     { const int rc_epoch = next_claim_epoch(c); if (rc_epoch) return rc_epoch; }
     a.claim_epoch = c->claim_epoch;
     // every strip's reset / spawn is complete before anybody's first phase touches it
-    peer_handshake_kernel<<<1, 1, 0, c->stream>>>(a.pv, a.pv.tag_base, &c->d_bar->abort);
+    peer_handshake_kernel<<<1, 1, 0, c->stream>>>(a.pv, a.pv.tag_base, reinterpret_cast<unsigned*>(c->d_flags + 2));
     c->launches++;
     void* args[] = {&a};
     const int grid = (int)std::max<size_t>(1, (n + ls.block - 1) / ls.block);
-    CU(cudaLaunchCooperativeKernel(ls.kernel, dim3(grid), dim3(ls.block), args, descend_smem(ls.block), c->stream));
+    CU(cudaLaunchCooperativeKernel(ls.kernel, dim3(grid), dim3(ls.block), args, ls.smem(ls.block), c->stream));
     c->launches++;
-    // a peer that never arrived aborts the launch; surface it with the next stats read
-    CU(cudaMemcpyAsync(c->d_flags + 2, &c->d_bar->abort, sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
     return SHX_OK;
   }
   if (n == 0) return SHX_OK;
@@ -705,6 +724,8 @@ static int run_device_drops(shx_ctx* c, size_t n, bool trace, bool align_age = f
     a.P = step_params(c->p);
     a.drops = c->d_drops + done;
     a.align_age = align_age ? 1u : 0u;
+    a.free_waits = (unsigned)c->cfg.free_waits;
+    a.abort_flag = c->d_flags + 2;  // OR-ed by the kernels (a later clean launch cannot clear it), reset by fetch_stats
     a.bar = c->d_bar;
     a.stats = c->d_stats;
     a.trace = (trace && done == 0) ? c->d_trace : nullptr;
@@ -715,25 +736,27 @@ static int run_device_drops(shx_ctx* c, size_t n, bool trace, bool align_age = f
     a.claim_epoch = c->claim_epoch;
     void* args[] = {&a};
     size_t take;
-    if (left <= 64 && !c->forced_shape) {
-      // a handful of drops: one CTA, the per-phase barrier is a plain __syncthreads
+    if (left <= 128 && !c->forced_shape) {
+      // a handful of drops: one CTA of eight lanes per drop, the per-phase barrier is a plain __syncthreads
       take = left;
       a.ndrops = (unsigned)take;
-      const int block = (int)((take + 31) / 32 * 32);
-      CU(cudaLaunchCooperativeKernel((void*)KERNEL_SMALL, dim3(1), dim3(block), args, descend_smem(block), c->stream));
+      const int block = (int)((take * 8 + 31) / 32 * 32);
+      CU(cudaLaunchCooperativeKernel((void*)KERNEL_SMALL, dim3(1), dim3(block), args, (size_t)kGroupSmemWords * 4 * block, c->stream));
     } else {
-      // dense shape once the spread shape would put more than ~4 CTAs of 64 on every SM
-      const LaunchShape& ls = c->shape[(left > (size_t)c->sm_count * 256) ? 1 : 0];
+      // eight lanes per drop while the whole batch is co-resident that way, one thread per drop beyond
+      const LaunchShape& g = c->shape[0];
+      const bool use_group = g.group && left <= (size_t)g.cap_blocks * g.drops_per_block(g.block);
+      const LaunchShape& ls = c->shape[(c->forced_shape || use_group) ? 0 : 1];
       const int block = ls.block;
       int cap = ls.cap_blocks;
       if (c->cfg.grid_blocks > 0) cap = std::min(cap, c->cfg.grid_blocks);
-      take = std::min(left, (size_t)cap * block);
+      const size_t per_block = ls.drops_per_block(block);
+      take = std::min(left, (size_t)cap * per_block);
       a.ndrops = (unsigned)take;
-      const int grid = (int)((take + block - 1) / block);
-      CU(cudaLaunchCooperativeKernel(ls.kernel, dim3(grid), dim3(block), args, descend_smem(block), c->stream));
+      const int grid = (int)((take + per_block - 1) / per_block);
+      CU(cudaLaunchCooperativeKernel(ls.kernel, dim3(grid), dim3(block), args, ls.smem(block), c->stream));
     }
     c->launches++;
-    CU(cudaMemcpyAsync(c->d_flags + 2, &c->d_bar->abort, sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
     done += take;
   }
   return SHX_OK;

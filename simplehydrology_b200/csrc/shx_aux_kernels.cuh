@@ -21,7 +21,12 @@ struct SpawnArgs {
   unsigned long long* stats;
 };
 
-__device__ __forceinline__ shx_drop make_drop(float x, float y, const MapView& m, int sequential, unsigned long long* stats) {
+// twin_rank: how many earlier drops of the batch were created on the bit-identical position.  Such copies have
+// identical state, hence identical claim keys, and would step together for their whole lives, each applying the full
+// erosion to the same cells; the k-th copy therefore starts with `waited` = min(k, 7) and the copies take their first
+// turns one after another (oracle: orc_ls_make_drops).
+__device__ __forceinline__ shx_drop make_drop(float x, float y, const MapView& m, int sequential, unsigned long long* stats,
+                                              unsigned twin_rank) {
   shx_drop d = {x, y, 0.0f, 0.0f, 1.0f, 0.0f, 0, SHX_DROP_ALIVE};  // water.h:14-23
   const int ix = (int)x, iy = (int)y;
   const bool oob = !(x > -1.0f) || !(y > -1.0f) || ix >= m.size || iy >= m.size;
@@ -29,16 +34,20 @@ __device__ __forceinline__ shx_drop make_drop(float x, float y, const MapView& m
     d.flags = 0;
     return d;
   }
-  float h = 0.0f;  // map.height() of a missing cell (cellpool.h:433-437)
-  if (!oob) {
-    const int4 hv = m.hq[(ix - m.xlo) * m.size + iy];
-    h = sequential ? __int_as_float(hv.x) : h_to_float(hv.x);
+  if (sequential) {
+    // world.h:71-72 tests the height when the drop is created, i.e. after the earlier drops of the call have run:
+    // descend_sequential_kernel applies the rejection (and counts it) right before the drop's first step
+    d.flags |= SHX_DROP_CHECK_SPAWN;
+    return d;
   }
+  float h = 0.0f;  // map.height() of a missing cell (cellpool.h:433-437)
+  if (!oob) h = h_to_float(m.hq[(ix - m.xlo) * m.size + iy].x);
   if (!above_tenth(h)) {  // world.h:71-72  (double)h < 0.1
     d.flags = SHX_DROP_REJECTED;
     atomicAdd(stats + ST_REJECTED, 1ull);
   } else {
     atomicAdd(stats + ST_SPAWNED, 1ull);
+    d.flags |= (int)(twin_rank < 7u ? twin_rank : 7u) << kWaitedShift;
   }
   return d;
 }
@@ -47,19 +56,47 @@ __global__ void spawn_kernel(const SpawnArgs a) {
   const unsigned n = a.nnodes * (unsigned)a.cycles;
   for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const unsigned node = a.node0 + k / (unsigned)a.cycles, i = (unsigned)a.i0 + k % (unsigned)a.cycles;
-    const uint64_t r = mix64(a.key + (((uint64_t)node << 32) | (uint64_t)i));
+    const uint64_t base = a.key + ((uint64_t)node << 32);
+    const uint64_t r = mix64(base + (uint64_t)i);
+    const uint32_t lx = (uint32_t)r % (uint32_t)a.tilesize, ly = (uint32_t)(r >> 32) % (uint32_t)a.tilesize;
+    unsigned twins = 0;  // earlier drops of this node's batch on the same cell (the node index decides the tile)
+    if (!a.sequential)
+      for (unsigned j = (unsigned)a.i0; j < i; j++) {
+        const uint64_t q = mix64(base + (uint64_t)j);
+        twins += ((uint32_t)q % (uint32_t)a.tilesize == lx && (uint32_t)(q >> 32) % (uint32_t)a.tilesize == ly) ? 1u : 0u;
+      }
     const int nx = (int)(node / (unsigned)a.mapsize) * a.tilesize, ny = (int)(node % (unsigned)a.mapsize) * a.tilesize;
-    const float x = (float)(nx + (int)((uint32_t)r % (uint32_t)a.tilesize));
-    const float y = (float)(ny + (int)((uint32_t)(r >> 32) % (uint32_t)a.tilesize));
+    const float x = (float)(nx + (int)lx);
+    const float y = (float)(ny + (int)ly);
     if (a.xy) { a.xy[2 * k] = x; a.xy[2 * k + 1] = y; }
-    a.drops[k] = make_drop(x, y, a.m, a.sequential, a.stats);
+    a.drops[k] = make_drop(x, y, a.m, a.sequential, a.stats, twins);
   }
 }
 
+// explicit spawn list: the twin rank of entry k is the number of earlier entries with the same bits (tiles of the
+// list staged through shared memory; O(n^2 / 2) compares, ~1 ms for the 131 072 drops of an 8192^2 cycle)
 __global__ void make_drops_kernel(const float* xy, unsigned n, const MapView m, int sequential, shx_drop* drops,
                                   unsigned long long* stats) {
-  for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
-    drops[k] = make_drop(xy[2 * k], xy[2 * k + 1], m, sequential, stats);
+  __shared__ uint2 s_xy[256];
+  const unsigned k0 = blockIdx.x * blockDim.x;
+  for (unsigned base = k0; base < n; base += gridDim.x * blockDim.x) {
+    const unsigned k = base + threadIdx.x;
+    uint2 me = make_uint2(0u, 0u);
+    if (k < n) me = make_uint2(__float_as_uint(xy[2 * k]), __float_as_uint(xy[2 * k + 1]));
+    unsigned twins = 0;
+    if (!sequential) {
+      const unsigned last = min(n, base + blockDim.x);  // entries before the last thread of this block
+      for (unsigned t0 = 0; t0 < last; t0 += 256u) {
+        __syncthreads();
+        const unsigned j = t0 + threadIdx.x;
+        if (threadIdx.x < 256u && j < n) s_xy[threadIdx.x] = make_uint2(__float_as_uint(xy[2 * j]), __float_as_uint(xy[2 * j + 1]));
+        __syncthreads();
+        const unsigned lim = k < n ? min(256u, k > t0 ? k - t0 : 0u) : 0u;
+        for (unsigned t = 0; t < lim; t++) twins += (s_xy[t].x == me.x && s_xy[t].y == me.y) ? 1u : 0u;
+      }
+    }
+    if (k < n) drops[k] = make_drop(xy[2 * k], xy[2 * k + 1], m, sequential, stats, twins);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

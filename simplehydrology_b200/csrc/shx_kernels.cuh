@@ -9,6 +9,7 @@
 //        {track_d, track_mx, track_my, pad}              int32 Q13.18 accumulators (RED targets)
 // Sequential mode stores fp32 heights in hq[].x and fp32 tracks in the record's second half.
 #pragma once
+#include <type_traits>
 #include "shx_step.cuh"
 
 namespace shx {
@@ -65,6 +66,8 @@ struct DescendArgs {
   unsigned ndrops;
   unsigned align_age;  // != 0: drops with age > 0 wait for the phase equal to their age
   unsigned claim_epoch;  // 1..15, top bits of every claim key of this launch (stale keys of earlier launches lose)
+  unsigned free_waits;   // waits per drop that do not cost it a step (shx_config.free_waits, <= 15)
+  int* abort_flag;       // context flag word, OR-ed (never overwritten): 1 = a peer timed out, 2 = phase limit
   GridBar* bar;
   unsigned long long* stats;
   float* trace;  // 7 floats per Drop::descend call of drop 0, or null
@@ -188,7 +191,7 @@ __device__ __forceinline__ unsigned peer_barrier_sum(GridBar* bar, const PeerVie
         if (!all && clock64() - t0 > 4000000000ll) dead = true;
       } while (!all && !dead);
       asm volatile("fence.acq_rel.sys;" ::: "memory");
-      if (dead) { total = 0; bar->abort = 1u; }
+      if (dead) { total = 0; bar->abort = 1u; }  // the caller ORs it into the context's flag word
       const unsigned long long rel = ((unsigned long long)total << 32) | tag;
       asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(&bar->release[par]), "l"(rel) : "memory");
       *s_total = total;
@@ -223,7 +226,7 @@ __global__ void peer_handshake_kernel(const PeerView pv, unsigned tag, unsigned*
     do {
       asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(slot) : "memory");
       if ((unsigned)got != tag && clock64() - t0 > 20000000000ll) {  // ~10 s: ranks may reach the call at different times
-        *abort_flag = 1u;
+        atomicOr(abort_flag, 1u);
         return;
       }
     } while ((unsigned)got != tag);
@@ -265,6 +268,24 @@ __device__ __forceinline__ unsigned claim_key(unsigned epoch, unsigned tag, cons
   h ^= h >> 15;
   const unsigned waited = ((unsigned)d.flags >> kWaitedShift) & 7u;
   return (epoch << 28) | (tag << 16) | (waited << 13) | (h & 0x1FFFu);
+}
+
+
+constexpr int kFreeWaitShift = 19;  // SHX_DROP_FREEW_SHIFT
+
+// A waiting phase (turn-taking): the wait counter of the key grows; the first free_waits waits of a drop's life are
+// free, every later one costs a step of its life (so a launch is bounded by maxAge + 2 + free_waits phases).
+// Returns true if the drop expired in the queue (water.h:74-77).
+__device__ __forceinline__ bool wait_one_phase(DropRegs& d, const DescendArgs& a) {
+  const unsigned waited = ((unsigned)d.flags >> kWaitedShift) & 7u;
+  d.flags = (d.flags & ~(7 << kWaitedShift)) | (int)((waited < 7u ? waited + 1u : 7u) << kWaitedShift);
+  const unsigned fw = ((unsigned)d.flags >> kFreeWaitShift) & 15u;
+  if (fw < a.free_waits) {
+    d.flags = (d.flags & ~(15 << kFreeWaitShift)) | (int)((fw + 1u) << kFreeWaitShift);
+    return false;
+  }
+  d.age++;
+  return (float)d.age > a.P.maxAge;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -485,14 +506,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
 
     if (kCoop) __syncwarp();  // the block rows written by the other lanes of the warp are complete
 
-    if (alive && !turn) {  // a drop with a higher key has the cell or stands next to it: wait
-      const unsigned waited = ((unsigned)d.flags >> kWaitedShift) & 7u;
-      d.flags = (d.flags & ~(7 << kWaitedShift)) | (int)((waited < 7u ? waited + 1u : 7u) << kWaitedShift);
-      // A phase spent waiting is a step of the drop's life not taken: the age advances, so a launch never
-      // needs more phases than maxAge + 2 however long the queues.  A drop that expires in the queue
-      // leaves its sediment where it stands (water.h:74-77).
-      d.age++;
-      if ((float)d.age > a.P.maxAge) {
+    if (alive && !turn) {  // a drop with a higher key has the cell: wait (the first free_waits waits are free, later ones cost a step)
+      if (wait_one_phase(d, a)) {  // expired in the queue: the sediment stays where the drop stands (water.h:74-77)
         const int q = h_quantize(d.sed);
         if (q && !SHX_EXP(2)) add32(h_at(ix, iy) + ww, q, ix);
         dC_prev = q;  // the other plane gets it in the next phase, like any other delta
@@ -628,7 +643,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
         float carried;
         // The exchange is halved for every cell around that holds a higher key: neighbouring cells that change
         // in the same phase form an explicit scheme whose factors (up to 1.1 per cell) must not add up.
-        const float dh = exchange_math(hc, h2, cap, mv.effD * damp, d, a.P, carried);  // water.h:127-136
+        const float dh = exchange_math<true>(hc, h2, cap, mv.effD * damp, d, a.P, carried);  // water.h:127-136
         const int q = h_quantize(dh);
         dC += q;
         fx_eroded -= (long long)q;
@@ -688,7 +703,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
       break;
     }
     if (phase + 2u >= kMaxPhases) {  // the claim tag would wrap: give up (the host reports SHX_ERR_RANGE)
-      if (gid == 0) a.bar->abort = 2u;
+      if (gid == 0) atomicOr(a.abort_flag, 2);
       break;
     }
   }
@@ -702,6 +717,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
     reinterpret_cast<float4*>(a.drops + gid)[1] = hi;
   }
   if (a.trace_n != nullptr && gid == 0) *a.trace_n = tn;
+  if (kPeer && gid == 0 && a.bar->abort) atomicOr(a.abort_flag, (int)a.bar->abort);
 
   // per-step counters: warp reduce, one atomic per warp
 #pragma unroll
@@ -743,6 +759,18 @@ __global__ void descend_sequential_kernel(const SequentialArgs a) {
   for (unsigned i = 0; i < a.ndrops; i++) {
     const shx_drop r = a.drops[i];
     DropRegs d = {r.px, r.py, r.sx, r.sy, r.volume, r.sediment, r.age, r.flags};
+    if (d.flags & SHX_DROP_CHECK_SPAWN) {  // world.h:71-74: the rejection sees what the earlier drops of the call left
+      d.flags &= ~SHX_DROP_CHECK_SPAWN;
+      const int sx = (int)d.px, sy = (int)d.py;
+      const bool oob = !(d.px > -1.0f) || !(d.py > -1.0f) || sx >= size || sy >= size;
+      const float h = oob ? 0.0f : H[4 * (sx * size + sy)];  // map.height() of a missing cell is 0 (cellpool.h:433-437)
+      if (!above_tenth(h)) {
+        d.flags = SHX_DROP_REJECTED;
+        a.stats[ST_REJECTED] += 1ull;
+      } else {
+        a.stats[ST_SPAWNED] += 1ull;
+      }
+    }
     while (d.flags & SHX_DROP_ALIVE) {
       const int ix = (int)d.px, iy = (int)d.py;
       const int cidx = ix * size + iy;
@@ -823,4 +851,5 @@ __global__ void descend_sequential_kernel(const SequentialArgs a) {
 
 }  // namespace shx
 
+#include "shx_descend.cuh"
 #include "shx_aux_kernels.cuh"

@@ -26,6 +26,7 @@ struct StepParams {
   float maxdiff, settling, lod, mapscale, lrate;
   float lim_axis, lim_diag;  // world.h:145: d*maxdiff*lodsize for d = 1 and d = sqrt(2)
   double keep;               // 1.0 - (double)evapRate, water.h:135-136
+  double inv_keep;           // 1.0 / keep: the batched kernels multiply where the reference divides
 };
 
 struct DropRegs {
@@ -126,6 +127,10 @@ __device__ __forceinline__ MoveResult move_math(const float hc, const float hxm,
 // water.h:127-136: hc = old cell's height, h2 = new cell's height (or hc - 0.002 when out of bounds,
 // water.h:121-122, done by the caller), cap = 1 + entrainment*erf(0.4*discharge) of the old cell
 // (water.h:127, cellpool.h:242-244).  Returns the fp32 amount to ADD to the old cell (-effD*cdiff).
+// kRecip: water.h:135 as a multiplication by the double 1/(1-evapRate) (batched mode; the fp64 division is a
+// ~50-instruction routine on the critical chain of every step; oracle: orc_ls_world.recip_evap).  The sequential
+// mode keeps the reference's division.
+template <bool kRecip = false>
 __device__ __forceinline__ float exchange_math(const float hc, const float h2, const float cap, const float effD, DropRegs& d,
                                                const StepParams& P, float& carried) {
   float c_eq = cap * (hc - h2);  // water.h:127-128
@@ -134,7 +139,7 @@ __device__ __forceinline__ float exchange_math(const float hc, const float h2, c
   const float e = effD * cdiff;
   d.sed += e;  // water.h:131
   carried = d.sed;
-  d.sed = (float)((double)d.sed / P.keep);  // water.h:135
+  d.sed = kRecip ? (float)((double)d.sed * P.inv_keep) : (float)((double)d.sed / P.keep);  // water.h:135
   d.vol = (float)((double)d.vol * P.keep);  // water.h:136
   return -e;                                // water.h:132
 }

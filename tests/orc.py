@@ -46,7 +46,7 @@ class SeqWorld(C.Structure):
 
 class LsWorld(C.Structure):
     _fields_ = [("p", Params), ("size", C.c_int), ("h", C.POINTER(C.c_int32) * 2), ("field", C.POINTER(C.c_float)),
-                ("track", C.POINTER(C.c_int32)), ("row0", C.c_int), ("row1", C.c_int), ("align_age", C.c_int), ("max_cycles_per_launch", C.c_int), ("exclusive_cells", C.c_int), ("cur_damp", C.c_float), ("free_waits", C.c_int), ("steps_per_phase", C.c_int)]
+                ("track", C.POINTER(C.c_int32)), ("row0", C.c_int), ("row1", C.c_int), ("align_age", C.c_int), ("max_cycles_per_launch", C.c_int), ("exclusive_cells", C.c_int), ("cur_damp", C.c_float), ("free_waits", C.c_int), ("recip_evap", C.c_int), ("steps_per_phase", C.c_int)]
 
 
 def build_oracle():

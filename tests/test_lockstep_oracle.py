@@ -115,10 +115,10 @@ def test_synth_terrain_is_normalised_and_seeded():
 
 
 def test_drops_on_one_cell_take_turns(init_cells):
-    """Turn-taking: of the drops standing on one cell (or next to a drop with a higher key) only one
-    steps per phase; the others wait, and a phase spent waiting is a step of their life not taken.  k drops spawned
-    on the same cell therefore leave it one after another, the call still ends after maxAge + 2 phases, and a drop
-    that is alone is not affected at all."""
+    """Turn-taking: of the drops standing on one cell only one steps per phase; the others wait.
+    The first free_waits (8) waits of a drop's life are free, every later one is a step of its life not taken.  k
+    drops spawned on the same cell therefore leave it one after another, the call ends after at most
+    maxAge + 2 + free_waits phases, and a drop that is alone is not affected at all."""
     p = orc.default_params(1)
     k = 5
     xy = np.tile(np.array([[256.25, 256.5]], np.float32), (k, 1))
@@ -131,8 +131,15 @@ def test_drops_on_one_cell_take_turns(init_cells):
     lone.upload(init_cells)
     d1, _ = lone.make_drops(xy[:1])
     s1, _ = lone.run_drops(d1)
-    assert st.phases == s1.phases == 502               # waiting does not prolong the call
-    assert (k - 1) * 100 < st.steps <= k * s1.steps - (k - 1)  # every drop went its way, minus the steps spent waiting
+    assert s1.phases == 502 and 502 < st.phases <= 502 + 8  # free waits prolong the call by at most free_waits
+    assert (k - 1) * 100 < st.steps <= k * s1.steps        # every drop went its way
+    # with no free waits a phase spent waiting costs a step, and the call never needs more than maxAge + 2 phases
+    paid = orc.Ls(p)
+    paid.upload(init_cells)
+    paid.w.contents.free_waits = 0
+    d0, _ = paid.make_drops(xy)
+    s0, _ = paid.run_drops(d0)
+    assert s0.phases == 502 and s0.steps <= k * s1.steps - (k - 1)
     assert st.term_age + st.term_vol + st.term_oob == k
     # without turn-taking all k step together in phase 0: no step is lost, but the first cell takes a k-fold hit
     free = orc.Ls(p)
@@ -140,10 +147,36 @@ def test_drops_on_one_cell_take_turns(init_cells):
     free.w.contents.exclusive_cells = 0
     d2, _ = free.make_drops(xy)
     s2, _ = free.run_drops(d2)
-    assert s2.steps > st.steps
+    assert s2.steps >= st.steps and s2.steps > s0.steps
     c0 = (256, 256)
     h0 = init_cells["height"][orc.tiled_index_map(p)[c0]]
     assert abs(free.height_q(0)[c0] * H_LSB - h0) > abs(ls.height_q(0)[c0] * H_LSB - h0) * 0.99  # no smaller hit
+
+
+def test_twins_take_turns(init_cells):
+    """Drops created on bit-identical positions have identical state and identical claim keys: without a tie-break
+    they would step together for life, each applying the full erosion.  The k-th copy starts with
+    waited = k, so the copies leave the cell one after another; the result does not depend on the list order."""
+    p = orc.default_params(1)
+    xy = np.array([[256.0, 256.0]] * 3 + [[100.0, 100.0], [300.0, 200.0], [100.0, 100.0]], np.float32)
+    ls = orc.Ls(p)
+    ls.upload(init_cells)
+    drops, _ = ls.make_drops(xy)
+    waited = (drops["flags"] >> 16) & 7
+    assert sorted(waited[:3]) == [0, 1, 2] and sorted(waited[[3, 5]]) == [0, 1] and waited[4] == 0
+    st, tr = ls.run_drops(drops.copy())
+    final = drops  # run a permuted list: same maps
+    ls2 = orc.Ls(p)
+    ls2.upload(init_cells)
+    d2, _ = ls2.make_drops(xy[::-1].copy())
+    st2, _ = ls2.run_drops(d2)
+    assert np.array_equal(ls.height_q(0), ls2.height_q(0)) and st.as_dict() == st2.as_dict()
+    # the copies did not march as one: their tracks differ from k times a lone drop's
+    lone = orc.Ls(p)
+    lone.upload(init_cells)
+    d1, _ = lone.make_drops(xy[:1])
+    lone.run_drops(d1)
+    assert not np.array_equal(ls.track_q()[200:320, 200:320, 0], 3 * lone.track_q()[200:320, 200:320, 0])
 
 
 def test_turn_taking_keeps_order_independence(init_cells):
