@@ -215,7 +215,12 @@ int shx_add_rootdensity(shx_ctx* c, const int* xy, const float* delta, size_t n)
  * uses after the unchanged Vegetation::grow() has edited the host pool. */
 int shx_set_rootdensity(shx_ctx* c, const int* xy, const float* value, size_t n);
 
-/* device-side seeded synthetic terrain (value-noise fBm normalised to [0,1]); other fields zeroed */
+/* == World::map.init(vertexpool, cellpool, SEED), cellpool.h:349-409 (SimpleHydrology.cpp:38): the reference's own
+ * terrain -- eight layers of FastNoiseLite 3-D OpenSimplex2 fBm, min/max normalised -- generated on the device, bit
+ * for bit the heights the reference computes on the host; all other fields zeroed (the reference leaves them
+ * uninitialised, cellpool.h:122). */
+int shx_init_terrain(shx_ctx* c, int seed);
+/* a cheaper device-side seeded synthetic terrain (value-noise fBm normalised to [0,1]); other fields zeroed */
 int shx_synth_terrain(shx_ctx* c, uint32_t seed);
 
 /* raw device state over the stored rows, cell index (x-xlo)*size+y (tests: bit-exact comparison

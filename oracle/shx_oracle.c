@@ -897,6 +897,121 @@ void orc_fill_tiled_from_planar(const orc_params* p, const float* planar, orc_ce
     }
 }
 
+
+/* ================================================================== terrain init (map::init, cellpool.h:349-409)
+ *
+ * Restates the noise the reference pulls from its vendored FastNoiseLite.h (source/include/FastNoiseLite.h, a
+ * header inside /root/reference, so it is pinned by the compiled reference itself: tests/test_oracle_golden.py
+ * compares with golden["init_height"], tests/test_oracle_vs_ref.py with a live 2048^2 init):
+ *   noise type OpenSimplex2, 3-D overload (z = SEED % 10000), default rotation  FastNoiseLite.h:322-338,687-716
+ *   fractal fBm with the constructor's defaults: 3 octaves, lacunarity 2, gain 0.5, bounding 1/1.75  :113-129,866-886
+ *   SingleOpenSimplex2 (3-D)  :1054-1148, GradCoord :541-552, Hash :487-504, FastRound :449-450
+ * Eight layers, frequency 1,2,..,128, weight 0.6^(o+1) accumulated in fp32 with the reference's double multiply
+ * (`scale *= 0.6`), then the min/max normalisation with both extremes starting at 0 (cellpool.h:382-408).
+ * All fp32, operation for operation, no contraction. */
+static float grad3(int g, int c) { /* component c of gradient g of FastNoiseLite's Gradients3D (64 x {x,y,z,0}) */
+  static const int special[4] = {8, 1, 9, 3};
+  const int b = g < 60 ? g % 12 : special[g - 60];
+  const int grp = b / 4, s = b % 4;
+  const float s1 = (s & 1) ? -1.0f : 1.0f, s2 = (s & 2) ? -1.0f : 1.0f;
+  if (grp == 0) return c == 0 ? 0.0f : (c == 1 ? s1 : s2);
+  if (grp == 1) return c == 1 ? 0.0f : (c == 0 ? s1 : s2);
+  return c == 2 ? 0.0f : (c == 0 ? s1 : s2);
+}
+
+#define FNL_PX 501125321
+#define FNL_PY 1136930381
+#define FNL_PZ 1720413743
+
+static int32_t imul(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); }
+static int32_t iadd(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
+static int32_t isub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
+static int fast_round(float f) { return f >= 0 ? (int)(f + 0.5f) : (int)(f - 0.5f); } /* :449-450 */
+
+static float grad_coord(int32_t seed, int32_t xp, int32_t yp, int32_t zp, float xd, float yd, float zd) { /* :541-552 */
+  int32_t hash = imul(seed ^ xp ^ yp ^ zp, 0x27d4eb2d); /* :496-504 */
+  hash ^= hash >> 15;
+  hash &= 63 << 2;
+  const int g = hash >> 2;
+  return xd * grad3(g, 0) + yd * grad3(g, 1) + zd * grad3(g, 2);
+}
+
+static float open_simplex2_3d(int32_t seed, float x, float y, float z) { /* :1054-1148 */
+  int32_t i = fast_round(x), j = fast_round(y), k = fast_round(z);
+  float x0 = (float)(x - (float)i), y0 = (float)(y - (float)j), z0 = (float)(z - (float)k);
+  int xs = (int)(-1.0f - x0) | 1, ys = (int)(-1.0f - y0) | 1, zs = (int)(-1.0f - z0) | 1;
+  float ax0 = (float)xs * -x0, ay0 = (float)ys * -y0, az0 = (float)zs * -z0;
+  i = imul(i, FNL_PX); j = imul(j, FNL_PY); k = imul(k, FNL_PZ);
+  float value = 0;
+  float a = (0.6f - x0 * x0) - (y0 * y0 + z0 * z0);
+  for (int l = 0;; l++) {
+    if (a > 0) value += (a * a) * (a * a) * grad_coord(seed, i, j, k, x0, y0, z0);
+    float b = a + 1;
+    int32_t i1 = i, j1 = j, k1 = k;
+    float x1 = x0, y1 = y0, z1 = z0;
+    if (ax0 >= ay0 && ax0 >= az0) { x1 += (float)xs; b -= (float)(xs * 2) * x1; i1 = isub(i1, imul(xs, FNL_PX)); }
+    else if (ay0 > ax0 && ay0 >= az0) { y1 += (float)ys; b -= (float)(ys * 2) * y1; j1 = isub(j1, imul(ys, FNL_PY)); }
+    else { z1 += (float)zs; b -= (float)(zs * 2) * z1; k1 = isub(k1, imul(zs, FNL_PZ)); }
+    if (b > 0) value += (b * b) * (b * b) * grad_coord(seed, i1, j1, k1, x1, y1, z1);
+    if (l == 1) break;
+    ax0 = 0.5f - ax0; ay0 = 0.5f - ay0; az0 = 0.5f - az0;
+    x0 = (float)xs * ax0; y0 = (float)ys * ay0; z0 = (float)zs * az0;
+    a += (0.75f - ax0) - (ay0 + az0);
+    i = iadd(i, (xs >> 1) & FNL_PX); j = iadd(j, (ys >> 1) & FNL_PY); k = iadd(k, (zs >> 1) & FNL_PZ);
+    xs = -xs; ys = -ys; zs = -zs;
+    seed = ~seed;
+  }
+  return value * 32.69428253173828125f;
+}
+
+/* GetNoise(x, y, z) of a noise object in the state map::init leaves it in (:322-338) */
+static float fnl_get_noise(float frequency, float x, float y, float z) {
+  x *= frequency; y *= frequency; z *= frequency; /* :689-691 */
+  {
+    const float R3 = (float)(2.0 / 3.0); /* :708-715 */
+    const float r = (x + y + z) * R3;
+    x = r - x; y = r - y; z = r - z;
+  }
+  int32_t seed = 1337; /* the constructor's default seed (:114), never changed by map::init */
+  float sum = 0;
+  float amp = 1 / 1.75f; /* mFractalBounding of the constructor (:129); SetFractalType does not recompute it */
+  for (int o = 0; o < 3; o++) { /* :872-882 with mWeightedStrength == 0: Lerp(1, ., 0) == 1 exactly */
+    const float noise = open_simplex2_3d(seed++, x, y, z);
+    sum += noise * amp;
+    amp *= 1.0f + 0.0f * ((noise + 1) * 0.5f - 1.0f);
+    x *= 2.0f; y *= 2.0f; z *= 2.0f;
+    amp *= 0.5f;
+  }
+  return sum;
+}
+
+float orc_init_raw_height(int x, int y, int tilesize, int seed) { /* cellpool.h:354-380 for one cell */
+  const float px = (float)x / (float)tilesize, py = (float)y / (float)tilesize; /* :370 */
+  const float z = (float)(seed % 10000);
+  float h = 0.0f, frequency = 1.0f, scale = 0.6f;
+  for (int o = 0; o < 8; o++) {
+    h += scale * fnl_get_noise(frequency, px, py, z); /* :371 */
+    frequency *= 2;                                   /* :375 */
+    scale = (float)((double)scale * 0.6);             /* :376 */
+  }
+  return h;
+}
+
+void orc_init_terrain(float* height, int mapsize, int tilesize, int seed) { /* planar x*size+y */
+  const int size = mapsize * tilesize;
+  float mn = 0.0f, mx = 0.0f; /* cellpool.h:382-383: both extremes start at 0 */
+#pragma omp parallel for reduction(min : mn) reduction(max : mx) schedule(static)
+  for (int x = 0; x < size; x++)
+    for (int y = 0; y < size; y++) {
+      const float v = orc_init_raw_height(x, y, tilesize, seed);
+      height[(size_t)x * size + y] = v;
+      mn = mn < v ? mn : v;
+      mx = mx > v ? mx : v;
+    }
+#pragma omp parallel for schedule(static)
+  for (size_t i = 0; i < (size_t)size * size; i++) height[i] = (height[i] - mn) / (mx - mn); /* :408 */
+}
+
 /* ---- per-frame views ------------------------------------------------------------------------ */
 
 /* node::height (cellpool.h:237-241): 0 outside the node */

@@ -158,6 +158,10 @@ void orc_ls_erode_spawnlist(orc_ls_world* w, const float* xy, size_t n, orc_stat
 
 /* ---- synthetic seeded terrain (value-noise fBm, normalised to [0,1]); planar x*size+y */
 void orc_synth_terrain(float* height, int size, uint32_t seed);
+/* map::init (cellpool.h:349-409): the reference's own terrain, 8 layers of 3-octave OpenSimplex2 fBm (vendored
+ * FastNoiseLite.h) normalised to [0,1]; planar x*size+y.  orc_init_raw_height is one cell before normalisation. */
+float orc_init_raw_height(int x, int y, int tilesize, int seed);
+void orc_init_terrain(float* height, int mapsize, int tilesize, int seed);
 /* planar -> tiled AoS heights (other fields zero) */
 /* quad::updatenode over every node (cellpool.h:286-305): 12 floats per cell {position, normal, tangent,
  * bitangent} in pool order, from the tiled AoS cells; node-local height()/normal() as in the reference */

@@ -114,6 +114,7 @@ def lib():
     L.shx_add_rootdensity.argtypes = [vp, vp, vp, sz]
     L.shx_set_rootdensity.argtypes = [vp, vp, vp, sz]
     L.shx_synth_terrain.argtypes = [vp, C.c_uint32]
+    L.shx_init_terrain.argtypes = [vp, C.c_int]
     L.shx_download_raw.argtypes = [vp, vp, vp]
     L.shx_stored_rows.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.shx_strip_pack_halo_delta.argtypes = [vp, vp, vp]
@@ -245,6 +246,10 @@ class World:
 
     def synth_terrain(self, seed):
         self._check(self.L.shx_synth_terrain(self._h, seed))
+
+    def init_terrain(self, seed):
+        """World::map.init(..., SEED) (cellpool.h:349-409) on the device"""
+        self._check(self.L.shx_init_terrain(self._h, seed))
 
     # -- the hot path
     def erode(self, cycles, seed=0):

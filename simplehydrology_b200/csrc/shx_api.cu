@@ -76,7 +76,7 @@ struct shx_ctx {
   uint64_t launches = 0;
   size_t last_n = 0;        // drops of the last run still sitting in d_drops
   bool tracks_clean = true; // all track accumulators are zero (world.h:56-61 already satisfied)
-  LaunchShape shape[2];     // multi-CTA launch shapes: [0] spread, [1] dense
+  LaunchShape shape[3];     // multi-CTA launch shapes: [0] group (eight lanes per drop), [1] spread, [2] dense
   bool forced_shape = false;
   // peer mode
   bool peer = false, peer_attached = false;
@@ -293,10 +293,11 @@ int shx_create(shx_ctx** out, const shx_params* p, const shx_config* cfg_in) {
     return fail(SHX_ERR_ARG, "peer mode does not take launch-shape overrides");
   }
   // shape[0] "group": eight lanes per drop in CTAs of 256 threads (32 drops), four CTAs per SM: batches of up to
-  // ~19 000 drops (latency regime: the reference's own sizes, the strips of a multi-GPU run); shape[1] "dense":
-  // one thread per drop, 2 x 448 threads per SM at 72 registers (throughput regime).  An explicit block_threads /
-  // variant / coop / grid_blocks in the config forces one shape for both (variant 5 = the group kernel).
-  for (int i = 0; i < 2; i++) {
+  // ~19 000 drops (latency regime: the reference's own sizes, the strips of a multi-GPU run); one thread per drop
+  // beyond that: shape[1] "spread", CTAs of 64 so that up to ~38 000 drops still cover all SMs, and shape[2]
+  // "dense", 2 x 448 threads per SM at 72 registers (throughput regime).  An explicit block_threads / variant /
+  // coop / grid_blocks in the config forces one shape for all (variant 5 = the group kernel).
+  for (int i = 0; i < 3; i++) {
     LaunchShape& ls = c->shape[i];
     if (forced && cfg.variant == 5) {
       ls.group = true;
@@ -312,9 +313,9 @@ int shx_create(shx_ctx** out, const shx_params* p, const shx_config* cfg_in) {
       ls.group = true;
       ls.block = 256;
       ls.kernel = (const void*)descend_group_kernel<256, 4>;
-    } else if (i == 0) {
+    } else if (i <= 1) {
       ls.block = 64;
-      ls.kernel = (const void*)descend_lockstep_kernel<128, 7, true, true>;
+      ls.kernel = peer ? (const void*)descend_lockstep_kernel<128, 7, true, true> : big_kernel(64, 2, true);
     } else {
       ls.block = 448;
       ls.kernel = peer ? (const void*)descend_lockstep_kernel<448, 2, true, true> : big_kernel(448, 3, true);
@@ -668,7 +669,7 @@ static int run_device_drops(shx_ctx* c, size_t n, bool trace, bool align_age = f
     // exactly ONE launch per call on every rank (even with no drops of its own): the kernels of
     // all ranks meet at every phase barrier
     if (!c->peer_attached) return fail(SHX_ERR_PEER, "shx_peer_attach has not been called");
-    const LaunchShape& ls = c->shape[(n > (size_t)c->sm_count * 256) ? 1 : 0];
+    const LaunchShape& ls = c->shape[(n > (size_t)c->sm_count * 256) ? 2 : 1];
     if (n > (size_t)ls.cap_blocks * ls.block) return fail(SHX_ERR_CAPACITY, "peer mode runs a call's drops in one launch");
     c->tracks_clean = false;
     DescendArgs a;
@@ -746,7 +747,7 @@ static int run_device_drops(shx_ctx* c, size_t n, bool trace, bool align_age = f
       // eight lanes per drop while the whole batch is co-resident that way, one thread per drop beyond
       const LaunchShape& g = c->shape[0];
       const bool use_group = g.group && left <= (size_t)g.cap_blocks * g.drops_per_block(g.block);
-      const LaunchShape& ls = c->shape[(c->forced_shape || use_group) ? 0 : 1];
+      const LaunchShape& ls = c->shape[(c->forced_shape || use_group) ? 0 : (left > (size_t)c->sm_count * 256 ? 2 : 1)];
       const int block = ls.block;
       int cap = ls.cap_blocks;
       if (c->cfg.grid_blocks > 0) cap = std::min(cap, c->cfg.grid_blocks);
@@ -962,6 +963,23 @@ int shx_synth_terrain(shx_ctx* c, uint32_t seed) {
   CU(cudaMemcpyAsync(c->d_u32, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
   synth_minmax_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->size, seed, c->d_u32);
   synth_fill_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->m, sequential(c) ? 1 : 0, seed, c->d_u32);
+  c->launches += 2;
+  c->tracks_clean = true;
+  CU(cudaGetLastError());
+  int rc = refresh_halo_ref(c);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  return SHX_OK;
+}
+
+int shx_init_terrain(shx_ctx* c, int seed) {  // map::init, cellpool.h:349-409
+  if (!c) return fail(SHX_ERR_ARG, "null context");
+  CU(cudaSetDevice(c->cfg.device));
+  const unsigned zero = 0x80000000u;  // f2ord(0.0f): both extremes start at 0 (cellpool.h:382-383)
+  const unsigned init[2] = {zero, zero};
+  CU(cudaMemcpyAsync(c->d_u32, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+  terrain_raw_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->m, c->p.tilesize, seed, c->d_u32);
+  terrain_fill_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->m, sequential(c) ? 1 : 0, c->d_u32);
   c->launches += 2;
   c->tracks_clean = true;
   CU(cudaGetLastError());

@@ -276,6 +276,128 @@ __global__ void synth_fill_kernel(const MapView m, int sequential, uint32_t seed
 }
 
 // ---------------------------------------------------------------------------------------------
+// N4: the reference's own terrain, map::init (cellpool.h:349-409): eight layers (frequency 1..128, weight
+// 0.6^(o+1)) of FastNoiseLite's 3-D OpenSimplex2 fBm (3 octaves, lacunarity 2, gain 0.5, bounding 1/1.75, default
+// rotation; vendored source/include/FastNoiseLite.h:322-338,687-716,866-886,1054-1148,541-552,487-504), z =
+// SEED % 10000, then the min/max normalisation with both extremes starting at 0.  fp32, operation for operation
+// (the library is built without FMA contraction), so the heights are the reference's to the bit
+// (oracle: orc_init_terrain, pinned against the compiled reference's own init).
+__device__ __forceinline__ float fnl_grad3(int g, int c) {  // component c of Gradients3D[g]: the 12 cube-edge vectors
+  const int b = g < 60 ? g % 12 : ((0x3918 >> (4 * (g - 60))) & 15);  // last four entries: 8, 1, 9, 3
+  const int grp = b >> 2;
+  const float s1 = (b & 1) ? -1.0f : 1.0f, s2 = (b & 2) ? -1.0f : 1.0f;
+  if (grp == 0) return c == 0 ? 0.0f : (c == 1 ? s1 : s2);
+  if (grp == 1) return c == 1 ? 0.0f : (c == 0 ? s1 : s2);
+  return c == 2 ? 0.0f : (c == 0 ? s1 : s2);
+}
+__device__ __forceinline__ float fnl_grad_coord(int seed, int xp, int yp, int zp, float xd, float yd, float zd) {
+  int hash = (int)((unsigned)(seed ^ xp ^ yp ^ zp) * 0x27d4eb2du);  // FastNoiseLite.h:496-504
+  hash ^= hash >> 15;                                               // :544-545
+  const int g = (hash & (63 << 2)) >> 2;
+  return xd * fnl_grad3(g, 0) + yd * fnl_grad3(g, 1) + zd * fnl_grad3(g, 2);
+}
+__device__ __forceinline__ int fnl_round(float f) { return f >= 0.0f ? (int)(f + 0.5f) : (int)(f - 0.5f); }  // :449-450
+
+__device__ float fnl_open_simplex2_3d(int seed, float x, float y, float z) {  // :1054-1148
+  constexpr unsigned PX = 501125321u, PY = 1136930381u, PZ = 1720413743u;
+  int i = fnl_round(x), j = fnl_round(y), k = fnl_round(z);
+  float x0 = x - (float)i, y0 = y - (float)j, z0 = z - (float)k;
+  int xs = (int)(-1.0f - x0) | 1, ys = (int)(-1.0f - y0) | 1, zs = (int)(-1.0f - z0) | 1;
+  float ax0 = (float)xs * -x0, ay0 = (float)ys * -y0, az0 = (float)zs * -z0;
+  i = (int)((unsigned)i * PX); j = (int)((unsigned)j * PY); k = (int)((unsigned)k * PZ);
+  float value = 0.0f;
+  float a = (0.6f - x0 * x0) - (y0 * y0 + z0 * z0);
+#pragma unroll 1
+  for (int l = 0;; l++) {
+    if (a > 0.0f) value += (a * a) * (a * a) * fnl_grad_coord(seed, i, j, k, x0, y0, z0);
+    float b = a + 1.0f;
+    int i1 = i, j1 = j, k1 = k;
+    float x1 = x0, y1 = y0, z1 = z0;
+    if (ax0 >= ay0 && ax0 >= az0) { x1 += (float)xs; b -= (float)(xs * 2) * x1; i1 = (int)((unsigned)i1 - (unsigned)xs * PX); }
+    else if (ay0 > ax0 && ay0 >= az0) { y1 += (float)ys; b -= (float)(ys * 2) * y1; j1 = (int)((unsigned)j1 - (unsigned)ys * PY); }
+    else { z1 += (float)zs; b -= (float)(zs * 2) * z1; k1 = (int)((unsigned)k1 - (unsigned)zs * PZ); }
+    if (b > 0.0f) value += (b * b) * (b * b) * fnl_grad_coord(seed, i1, j1, k1, x1, y1, z1);
+    if (l == 1) break;
+    ax0 = 0.5f - ax0; ay0 = 0.5f - ay0; az0 = 0.5f - az0;
+    x0 = (float)xs * ax0; y0 = (float)ys * ay0; z0 = (float)zs * az0;
+    a += (0.75f - ax0) - (ay0 + az0);
+    i = (int)((unsigned)i + ((unsigned)(xs >> 1) & PX)); j = (int)((unsigned)j + ((unsigned)(ys >> 1) & PY));
+    k = (int)((unsigned)k + ((unsigned)(zs >> 1) & PZ));
+    xs = -xs; ys = -ys; zs = -zs;
+    seed = ~seed;
+  }
+  return value * 32.69428253173828125f;
+}
+
+__device__ float terrain_raw(int x, int y, int tilesize, int seed) {  // cellpool.h:354-380 for one cell
+  const float px = (float)x / (float)tilesize, py = (float)y / (float)tilesize;  // :370
+  const float pz = (float)(seed % 10000);
+  float h = 0.0f, frequency = 1.0f, scale = 0.6f;
+#pragma unroll 1
+  for (int o = 0; o < 8; o++) {
+    float fx = px * frequency, fy = py * frequency, fz = pz * frequency;  // FastNoiseLite.h:689-691
+    const float r = (fx + fy + fz) * (float)(2.0 / 3.0);                  // :708-715
+    fx = r - fx; fy = r - fy; fz = r - fz;
+    int s = 1337;             // the constructor's seed (:114)
+    float sum = 0.0f, amp = 1.0f / 1.75f;  // :129
+#pragma unroll 1
+    for (int i = 0; i < 3; i++) {  // :872-882 (weighted strength 0: the Lerp factor is exactly 1)
+      const float noise = fnl_open_simplex2_3d(s++, fx, fy, fz);
+      sum += noise * amp;
+      amp *= 1.0f + 0.0f * ((noise + 1.0f) * 0.5f - 1.0f);
+      fx *= 2.0f; fy *= 2.0f; fz *= 2.0f;
+      amp *= 0.5f;
+    }
+    h += scale * sum;                      // cellpool.h:371
+    frequency *= 2.0f;                     // :375
+    scale = (float)((double)scale * 0.6);  // :376
+  }
+  return h;
+}
+
+// pass 1: raw heights of the stored rows (parked in hq[].x as float bits) and min/max over the WHOLE map (every
+// strip computes the same pair; rows of other strips are evaluated for the extremes only)
+__global__ void terrain_raw_kernel(const MapView m, int tilesize, int seed, unsigned* mnmx) {
+  unsigned mn = 0xffffffffu, mx = 0u;
+  const size_t n = (size_t)m.size * m.size;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i / m.size), y = (int)(i % m.size);
+    const float v = terrain_raw(x, y, tilesize, seed);
+    if (x >= m.xlo && x < m.xlo + m.nrows) m.hq[(size_t)(x - m.xlo) * m.size + y].x = __float_as_int(v);
+    const unsigned o = f2ord(v + 0.0f);
+    mn = min(mn, o);
+    mx = max(mx, o);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(mnmx, mn);
+    atomicMax(mnmx + 1, mx);
+  }
+}
+
+// pass 2: (h - min) / (max - min), cellpool.h:408; all other fields zero
+__global__ void terrain_fill_kernel(const MapView m, int sequential, const unsigned* mnmx) {
+  const float mn = ord2f(mnmx[0]), mx = ord2f(mnmx[1]);
+  const float range = mx - mn;
+  const size_t n = (size_t)m.nrows * m.size;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float h = (__int_as_float(m.hq[i].x) - mn) / range;
+    reinterpret_cast<int4*>(m.rec + i)[0] = make_int4(0, 0, 0, 0);
+    reinterpret_cast<int4*>(m.rec + i)[1] = make_int4(0, 0, 0, 0);
+    if (sequential) {
+      m.hq[i] = make_int4(__float_as_int(h), 0, 0, 0);
+    } else {
+      const int32_t q = h_quantize(h);
+      m.hq[i] = make_int4(q, 0, q, 0);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Row-strip exchange helpers (multi-GPU).  A strip keeps `halo` rows of its neighbours' heights on
 // each side.  Cascade transfers of drops on the strip's boundary rows land in those halo rows;
 // `halo_ref` remembers what the halo held at the last refresh, so (current - ref) is exactly the

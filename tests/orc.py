@@ -153,6 +153,17 @@ def synth_terrain(size, seed):
     return h
 
 
+def init_terrain(mapsize, seed, tilesize=512):
+    """map::init (cellpool.h:349-409) restated: planar heights of the reference's own terrain"""
+    size = mapsize * tilesize
+    h = np.empty((size, size), np.float32)
+    L = lib()
+    L.orc_init_terrain.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.orc_init_terrain.restype = None
+    L.orc_init_terrain(h.ctypes.data, mapsize, tilesize, seed)
+    return h
+
+
 class Seq:
     """sequential fp32 oracle over a tiled AoS cell buffer (numpy structured array)"""
 

@@ -101,3 +101,30 @@ def test_gather_cells_returns_records_and_map_normals(golden, init_cells):
     S = orc.Seq(full.copy(), params=p)
     want = np.stack([S.normal(int(x), int(y)) for x, y in xy])
     assert np.array_equal(nrm + np.float32(0.0), want + np.float32(0.0))
+
+
+@pytest.mark.parametrize("mapsize,seed,tilesize", [(1, 1, 512), (2, 20007, 512), (3, 5, 64)])
+def test_device_terrain_init_is_the_references(mapsize, seed, tilesize, golden):
+    """shx_init_terrain = World::map.init (cellpool.h:349-409) on the device: the Q5.26 heights are the quantised
+    heights of the restated (and reference-pinned) init, every other field zero; seed 1 is ./hydrology 1 itself"""
+    p = shx.default_params(mapsize)
+    p.tilesize = tilesize
+    with shx.World(params=p) as W:
+        W.init_terrain(seed)
+        h0, h1, f, t = W.download_raw()
+        cells = W.download()
+    want = orc.init_terrain(mapsize, seed, tilesize)
+    q = np.rint(want.astype(np.float64) * 2 ** 26).astype(np.int32)
+    assert np.array_equal(h0, q) and np.array_equal(h1, q)
+    assert not f.any() and not t.any()
+    if (mapsize, seed, tilesize) == (1, 1, 512):
+        ref = golden["init_height"].reshape(512, 512)
+        assert np.abs(cells["height"].reshape(512, 512) - ref).max() <= 2.0 ** -27
+        assert int((cells["height"] < 0.1).sum()) == 805  # SURVEY.md 8c probe figure
+
+
+def test_device_terrain_init_in_sequential_mode_is_bit_exact(golden):
+    with shx.World(mapsize=1, mode=shx.MODE_SEQUENTIAL) as W:
+        W.init_terrain(1)
+        cells = W.download()
+    assert np.array_equal(cells["height"].view(np.uint32), golden["init_height"].view(np.uint32))

@@ -174,3 +174,12 @@ def test_vertex_fill_matches_reference_updatenode(golden, init_cells):
         assert np.array_equal(bits(v[golden["vertex_sample_idx"]]), bits(golden[f"vertex_{tag}_sample"])), tag
         assert np.array_equal(sha(v), golden[f"vertex_{tag}_sha"]), tag
         S.erode_spawnlist(golden["spawn_lists"][0])
+
+
+def test_terrain_init_restatement_reproduces_the_reference_world(golden):
+    """orc_init_terrain (map::init restated, cellpool.h:349-409 + the vendored FastNoiseLite.h) against the heights
+    the compiled reference produced for ./hydrology 1: bit-identical, incl. the survey's probe figures"""
+    got = orc.init_terrain(1, 1)
+    want = golden["init_height"].reshape(512, 512)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert int((got < 0.1).sum()) == 805 and abs(float(got.mean()) - 0.494445) < 1e-6 and got.min() == 0.0 and got.max() == 1.0

@@ -90,3 +90,23 @@ def test_vertex_fill_restatement_matches_updatenode(mapsize):
     if not orc.have_ref(mapsize):
         pytest.skip("oracle/_ref for this map size not built")
     assert orc.run_ref_script(VERTEX_SCRIPT % (mapsize, mapsize)).strip().endswith("OK")
+
+
+INIT_SCRIPT = r"""
+import numpy as np, orc
+R = orc.Ref(%d, seed=%d)
+p = orc.default_params(%d)
+want = orc.tiled_to_planar(p, R.cells)
+got = orc.init_terrain(%d, %d)
+print("OK" if np.array_equal(want.view(np.uint32), got.view(np.uint32)) else "MISMATCH", float(np.abs(want - got).max()))
+"""
+
+
+@pytest.mark.parametrize("mapsize,seed", [(1, 7), (1, 12345), (4, 1)])
+def test_terrain_init_restatement_matches_map_init(mapsize, seed):
+    """map::init (cellpool.h:349-409, FastNoiseLite OpenSimplex2 fBm) through the compiled reference vs
+    orc_init_terrain: bit-identical heights, also for a seed above 10000 (SEED % 10000) and a tiled 2048^2 map"""
+    if not orc.have_ref(mapsize):
+        pytest.skip("oracle/_ref for this map size not built")
+    out = orc.run_ref_script(INIT_SCRIPT % (mapsize, seed, mapsize, mapsize, seed))
+    assert out.strip().startswith("OK"), out

@@ -1,5 +1,5 @@
 """Development aid: time erode(512) for several descend-kernel launch shapes.
-usage: python tools/tune_descend.py MAPSIZE [block:variant:grid ...]"""
+usage: python tools/tune_descend.py MAPSIZE [block:variant:grid[:coop[:cycles]] ...]"""
 import os
 import sys
 
@@ -26,7 +26,7 @@ def run(ms, block, variant, grid, coop=0, cycles=512, warm=4, n=6):
     t = e0.elapsed_time(e1) / n
     st = W.erode(cycles, 1)
     W.close()
-    print(f"mapsize {ms} block {block} variant {variant} grid {grid} coop {coop}: {t:.3f} ms/cycle  {t*1e3/max(st.phases,1):.2f} us/phase  "
+    print(f"mapsize {ms} block {block} variant {variant} grid {grid} coop {coop} cycles {cycles}: {t:.3f} ms/cycle  {t*1e3/max(st.phases,1):.2f} us/phase  "
           f"{st.steps/(t*1e-3)/1e9:.3f} Gsteps/s  launches {st.launches}", flush=True)
 
 
@@ -34,5 +34,5 @@ if __name__ == "__main__":
     ms = int(sys.argv[1])
     cfgs = sys.argv[2:] or ["256:0:0"]
     for c in cfgs:
-        b, v, g, co = (int(x) for x in (c.split(":") + ["0"])[:4])
-        run(ms, b, v, g, co)
+        b, v, g, co, cy = (int(x) for x in (c.split(":") + ["0", "512"])[:5]) if c.count(":") < 4 else (int(x) for x in c.split(":"))
+        run(ms, b, v, g, co, cycles=cy)
