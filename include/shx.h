@@ -144,6 +144,10 @@ typedef struct {
    * queues in river cells cost the drops ~3 % of their steps, with 8 free waits ~1 %).  A launch needs at most
    * maxAge + 2 + free_waits phases. */
   int free_waits;
+  /* 1: do not put the height / claim words under a persisting-L2 access-policy window.  By default a context whose
+   * words fit the device's persisting L2 carve-out (<= 2048^2 on B200) launches its descend kernels with such a
+   * window, so the streaming passes between calls cannot evict what every phase gathers. */
+  int no_l2_window;
 } shx_config;
 
 /* CUDA IPC handles of one rank's strip (opaque bytes; gather them from all ranks with the caller's
@@ -195,6 +199,9 @@ int shx_read_stats(shx_ctx* c, shx_stats* out);             /* syncs; stats of t
 typedef struct {
   double spawn_ms, descend_ms, ema_ms;
   uint64_t descend_launches; /* timed descend spans (one per erode call) */
+  double pack_ms;  /* shx_download: device layout -> tiled AoS staging tiles (sum over tiles) */
+  double d2h_ms;   /* shx_download: the device-to-host copies on the copy stream (sum over tiles; overlaps pack_ms) */
+  double push_ms;  /* shx_add/set_rootdensity: host-to-device copy + kernel */
 } shx_timing;
 int shx_timing_enable(shx_ctx* c, int on);
 int shx_timing_read(shx_ctx* c, shx_timing* out);
@@ -285,6 +292,34 @@ int shx_strip_erode_begin(shx_ctx* c, int cycles, uint64_t seed);
  * neighbours handed over at the end of the previous call, when strips exchange once per call */
 int shx_strip_erode_begin_with(shx_ctx* c, int cycles, uint64_t seed, const shx_drop* dev_carried, size_t n_carried);
 int shx_strip_erode_end(shx_ctx* c);
+
+/* ---- multi-GPU from ONE host thread: what the reference's single frame loop (SimpleHydrology.cpp:314-324) can call.
+ * shx_multi owns one strip context per device (row strips of whole tile rows: mapsize must be divisible by ngpu).
+ * shx_multi_erode == World::erode(cycles) on all strips at once; the strips meet ONCE per call: each strip's pack
+ * kernels store its message (border-crossing drops, the height deltas it put into its halo rows, its edge rows)
+ * straight into the neighbour's inbox over NVLink (peer access; cudaMemcpyPeerAsync where a pair of devices has
+ * none), CUDA events order pack -> apply across devices, no collective and no host wait inside a call.  A drop that
+ * leaves its strip pauses until the next call.  Deterministic for a given ngpu; statistically (not bitwise) the
+ * single-GPU result (tests/test_gpu_strips.py, tests/test_gpu_multi.py).  `devices` == NULL: ordinals 0..ngpu-1
+ * (wrapping around the visible devices, so k logical strips can share one GPU); `base` may be NULL.
+ * cycles must not exceed max_cycles_per_launch (512) when ngpu > 1.  ngpu == 1 is a plain whole-map context. */
+typedef struct shx_multi shx_multi;
+const char* shx_multi_last_error(void);
+int shx_multi_create(shx_multi** out, const shx_params* p, int ngpu, const int* devices, const shx_config* base);
+void shx_multi_destroy(shx_multi* m);
+int shx_multi_strips(const shx_multi* m);
+shx_ctx* shx_multi_strip(shx_multi* m, int i); /* the i-th strip's context (views, gathers, timing ...) */
+int shx_multi_upload(shx_multi* m, const shx_cell* pool, size_t ncells);
+int shx_multi_download(shx_multi* m, shx_cell* pool, size_t ncells, unsigned field_mask); /* all devices copy concurrently */
+int shx_multi_init_terrain(shx_multi* m, int seed);
+int shx_multi_synth_terrain(shx_multi* m, uint32_t seed);
+int shx_multi_set_params(shx_multi* m, const shx_params* p);
+int shx_multi_set_rootdensity(shx_multi* m, const int* xy, const float* value, size_t n);
+int shx_multi_erode(shx_multi* m, int cycles, uint64_t seed, shx_stats* out /* summed over strips; may be NULL */);
+int shx_multi_erode_async(shx_multi* m, int cycles, uint64_t seed);
+int shx_multi_read_stats(shx_multi* m, shx_stats* out);
+int shx_multi_in_flight(shx_multi* m, size_t* ndrops); /* drops waiting for the next call */
+int shx_multi_sync(shx_multi* m);
 
 /* ---- peer mode (shx_config.peer_world > 1): export this rank's strip, map everybody's */
 int shx_peer_export(shx_ctx* c, shx_peer_handles* out);

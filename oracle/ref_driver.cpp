@@ -185,6 +185,22 @@ int ref_oob(float x, float y) { return World::map.oob(glm::vec2(x, y)) ? 1 : 0; 
 
 // updatenode (cellpool.h:286-305) over every node; out receives 12 floats per
 // cell in pool order (node-major, then x*tilesize+y), i.e. the Vertex records.
+// The reference's own frame (SimpleHydrology.cpp:319-320): World::erode(cycles) then Vegetation::grow(), both
+// drawing from the global rand() stream like the application.
+void ref_frame(int cycles) {
+  World::erode(cycles);
+  Vegetation::grow();
+}
+void ref_vegetation_grow() { Vegetation::grow(); }  // vegetation.h:122-188
+size_t ref_plant_count() { return Vegetation::plants.size(); }
+void ref_plants(float* out3) {  // {pos.x, pos.y, size} per plant
+  for (size_t i = 0; i < Vegetation::plants.size(); i++) {
+    out3[3 * i] = Vegetation::plants[i].pos.x;
+    out3[3 * i + 1] = Vegetation::plants[i].pos.y;
+    out3[3 * i + 2] = Vegetation::plants[i].size;
+  }
+}
+
 void ref_update_vertices(float* out) {
   for (auto& node : World::map.nodes) quad::updatenode(vertexpool, node);
   memcpy(out, vertexpool.store.data(), sizeof(Vertex) * (size_t)quad::area);

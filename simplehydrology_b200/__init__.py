@@ -46,7 +46,7 @@ class Config(C.Structure):
     _fields_ = [("device", C.c_int), ("mode", C.c_int), ("row0", C.c_int), ("row1", C.c_int), ("halo", C.c_int),
                 ("max_drops", C.c_size_t), ("block_threads", C.c_int), ("grid_blocks", C.c_int), ("variant", C.c_int),
                 ("keep_tracks", C.c_int), ("coop", C.c_int), ("peer_rank", C.c_int), ("peer_world", C.c_int),
-                ("max_cycles_per_launch", C.c_int), ("free_waits", C.c_int)]
+                ("max_cycles_per_launch", C.c_int), ("free_waits", C.c_int), ("no_l2_window", C.c_int)]
 
 
 class PeerHandles(C.Structure):
@@ -67,7 +67,7 @@ class Stats(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("spawn_ms", C.c_double), ("descend_ms", C.c_double), ("ema_ms", C.c_double),
-                ("descend_launches", C.c_uint64)]
+                ("descend_launches", C.c_uint64), ("pack_ms", C.c_double), ("d2h_ms", C.c_double), ("push_ms", C.c_double)]
 
 
 _lib = None
@@ -113,6 +113,24 @@ def lib():
     L.shx_run_drops.argtypes = [vp, vp, sz, C.POINTER(Stats)]
     L.shx_add_rootdensity.argtypes = [vp, vp, vp, sz]
     L.shx_set_rootdensity.argtypes = [vp, vp, vp, sz]
+    L.shx_multi_last_error.restype = C.c_char_p
+    L.shx_multi_create.argtypes = [C.POINTER(vp), C.POINTER(Params), C.c_int, vp, C.POINTER(Config)]
+    L.shx_multi_destroy.argtypes = [vp]
+    L.shx_multi_destroy.restype = None
+    L.shx_multi_strips.argtypes = [vp]
+    L.shx_multi_strip.argtypes = [vp, C.c_int]
+    L.shx_multi_strip.restype = vp
+    L.shx_multi_upload.argtypes = [vp, vp, sz]
+    L.shx_multi_download.argtypes = [vp, vp, sz, C.c_uint]
+    L.shx_multi_init_terrain.argtypes = [vp, C.c_int]
+    L.shx_multi_synth_terrain.argtypes = [vp, C.c_uint32]
+    L.shx_multi_set_params.argtypes = [vp, C.POINTER(Params)]
+    L.shx_multi_set_rootdensity.argtypes = [vp, vp, vp, sz]
+    L.shx_multi_erode.argtypes = [vp, C.c_int, u64, C.POINTER(Stats)]
+    L.shx_multi_erode_async.argtypes = [vp, C.c_int, u64]
+    L.shx_multi_read_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.shx_multi_in_flight.argtypes = [vp, C.POINTER(sz)]
+    L.shx_multi_sync.argtypes = [vp]
     L.shx_synth_terrain.argtypes = [vp, C.c_uint32]
     L.shx_init_terrain.argtypes = [vp, C.c_int]
     L.shx_download_raw.argtypes = [vp, vp, vp]
@@ -156,7 +174,7 @@ class World:
 
     def __init__(self, params=None, mapsize=1, mode=MODE_BATCHED, device=0, row0=0, row1=0, halo=2, max_drops=0,
                  block_threads=0, grid_blocks=0, variant=0, keep_tracks=0, coop=0, peer_rank=0, peer_world=0,
-                 max_cycles_per_launch=0, free_waits=None):
+                 max_cycles_per_launch=0, free_waits=None, no_l2_window=0):
         self.L = lib()
         self.params = params if params is not None else default_params(mapsize)
         cfg = Config()
@@ -168,6 +186,7 @@ class World:
         cfg.max_cycles_per_launch = max_cycles_per_launch
         if free_waits is not None:
             cfg.free_waits = free_waits
+        cfg.no_l2_window = no_l2_window
         self.cfg = cfg
         self.size = self.params.mapsize * self.params.tilesize
         self.ncells = self.size * self.size
@@ -399,3 +418,107 @@ class World:
         st = Stats()
         self._check(self.L.shx_strip_run_device_drops(self._h, dev_ptr, n, C.byref(st) if want_stats else None))
         return st
+
+
+class _StripView(World):
+    """a strip context owned by a MultiWorld: the World methods over a borrowed handle"""
+
+    def __init__(self, L, handle, params, cfg):
+        self.L, self._h, self.params, self.cfg = L, handle, params, cfg
+        self.size = params.mapsize * params.tilesize
+        self.ncells = self.size * self.size
+
+    def close(self):
+        self._h = None  # owned by the MultiWorld
+
+
+class MultiWorld:
+    """One world over `ngpu` row strips driven by ONE host thread through shx_multi (include/shx.h): the strips
+    exchange once per erode call by peer stores into the neighbours' inboxes.  `devices` may repeat an ordinal
+    (k logical strips on one GPU)."""
+
+    def __init__(self, params=None, mapsize=1, ngpu=1, devices=None, **cfg_kw):
+        self.L = lib()
+        self.params = params if params is not None else default_params(mapsize)
+        self.size = self.params.mapsize * self.params.tilesize
+        self.ncells = self.size * self.size
+        cfg = Config()
+        self.L.shx_default_config(C.byref(cfg))
+        for k, v in cfg_kw.items():
+            setattr(cfg, k, v)
+        dev = (C.c_int * ngpu)(*devices) if devices is not None else None
+        h = C.c_void_p()
+        self._h = None
+        self._check(self.L.shx_multi_create(C.byref(h), C.byref(self.params), ngpu, dev, C.byref(cfg)))
+        self._h = h
+        self.ngpu = ngpu
+        rows = (self.params.mapsize // ngpu) * self.params.tilesize
+        self.strips = []
+        for i in range(ngpu):
+            c = Config.from_buffer_copy(bytes(cfg))
+            if ngpu > 1:
+                c.row0, c.row1 = i * rows, (i + 1) * rows
+            self.strips.append(_StripView(self.L, C.c_void_p(self.L.shx_multi_strip(self._h, i)), self.params, c))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise ShxError(rc, self.L.shx_multi_last_error().decode())
+
+    def close(self):
+        if self._h:
+            self.L.shx_multi_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, cells):
+        assert cells.dtype == CELL_DTYPE and cells.size == self.ncells and cells.flags.c_contiguous
+        self._check(self.L.shx_multi_upload(self._h, cells.ctypes.data, cells.size))
+
+    def download(self, out=None, mask=F_ALL):
+        if out is None:
+            out = np.zeros(self.ncells, CELL_DTYPE)
+        self._check(self.L.shx_multi_download(self._h, out.ctypes.data, out.size, mask))
+        return out
+
+    def init_terrain(self, seed):
+        self._check(self.L.shx_multi_init_terrain(self._h, seed))
+
+    def synth_terrain(self, seed):
+        self._check(self.L.shx_multi_synth_terrain(self._h, seed))
+
+    def set_rootdensity(self, xy, value):
+        xy = np.ascontiguousarray(xy, np.int32)
+        value = np.ascontiguousarray(value, np.float32)
+        self._check(self.L.shx_multi_set_rootdensity(self._h, xy.ctypes.data, value.ctypes.data, value.size))
+
+    def erode(self, cycles, seed=0):
+        st = Stats()
+        self._check(self.L.shx_multi_erode(self._h, cycles, seed, C.byref(st)))
+        return st
+
+    def erode_async(self, cycles, seed=0):
+        self._check(self.L.shx_multi_erode_async(self._h, cycles, seed))
+
+    def read_stats(self):
+        st = Stats()
+        self._check(self.L.shx_multi_read_stats(self._h, C.byref(st)))
+        return st
+
+    def in_flight(self):
+        n = C.c_size_t()
+        self._check(self.L.shx_multi_in_flight(self._h, C.byref(n)))
+        return n.value
+
+    def sync(self):
+        self._check(self.L.shx_multi_sync(self._h))

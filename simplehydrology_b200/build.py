@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libshx.so")
-SOURCES = [os.path.join(HERE, "csrc", "shx_api.cu")]
+SOURCES = [os.path.join(HERE, "csrc", "shx_api.cu"), os.path.join(HERE, "csrc", "shx_multi.cu")]
 DEPS = sorted(os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc")) if f.endswith((".cu", ".cuh", ".h"))) + \
        [os.path.join(ROOT, "include", "shx.h")]
 

@@ -22,7 +22,7 @@ struct LaunchShape {
 };
 
 struct TimingSpan {
-  int kind;  // 0 spawn, 1 descend, 2 ema
+  int kind;  // 0 spawn, 1 descend, 2 ema, 3 pack (download), 4 device-to-host copy, 5 rootdensity push
   cudaEvent_t e0, e1;
 };
 
@@ -70,6 +70,9 @@ struct shx_ctx {
   unsigned* d_u32 = nullptr;  // [0..1] min/max, [2..3] migrant counts
   int32_t* d_halo_ref[2] = {nullptr, nullptr};
   shx_cell* d_stage = nullptr;
+  shx_cell* d_stage2 = nullptr;      // second tile staging buffer: the pack of tile t+1 overlaps the DMA of tile t
+  cudaStream_t copy_stream = nullptr;  // device-to-host copies of shx_download
+  cudaEvent_t ev_packed[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
   cudaStream_t stream = nullptr;  // legacy default stream unless set
   int sm_count = 0;
   uint64_t epoch = 0;
@@ -88,6 +91,15 @@ struct shx_ctx {
   bool timing = false;
   std::vector<TimingSpan> spans;
   bool strip_open = false;  // between shx_strip_erode_begin and _end
+  // sparse pushes (Plant::root edits): persistent device list + pinned bounce buffer, so that a push is two async
+  // copies and a launch (round 1 allocated and freed with the stream-ordered allocator and synchronised per call:
+  // with the pool's default release threshold that was a real cudaMalloc/cudaFree pair every frame)
+  char* d_push = nullptr;
+  char* h_push = nullptr;  // pinned
+  size_t push_cap = 0;
+  cudaEvent_t push_done = nullptr;  // the bounce buffer may be overwritten once this has fired
+  cudaAccessPolicyWindow l2_window{};  // persisting-L2 window over the height / claim words (maps that fit)
+  bool l2_window_on = false;
 };
 
 static StepParams step_params(const shx_params& p) {
@@ -170,10 +182,19 @@ void shx_destroy(shx_ctx* c) {
   cudaFree(c->d_drops); cudaFree(c->d_xy); cudaFree(c->d_bar); cudaFree(c->d_stats); cudaFree(c->d_flags);
   cudaFree(c->d_trace); cudaFree(c->d_u32); cudaFree(c->d_halo_ref[0]); cudaFree(c->d_halo_ref[1]);
   cudaFree(c->d_stage);
+  cudaFree(c->d_stage2);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  for (int i = 0; i < 2; i++) {
+    if (c->ev_packed[i]) cudaEventDestroy(c->ev_packed[i]);
+    if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+  }
   for (void* p : c->peer_opened)
     if (p) cudaIpcCloseMemHandle(p);
   cudaFree(c->d_inbox);
   cudaFree(c->d_view);
+  cudaFree(c->d_push);
+  if (c->h_push) cudaFreeHost(c->h_push);
+  if (c->push_done) cudaEventDestroy(c->push_done);
   if (c->h_stats) cudaFreeHost(c->h_stats);
   if (c->h_flags) cudaFreeHost(c->h_flags);
   delete c;
@@ -264,6 +285,21 @@ int shx_create(shx_ctx** out, const shx_params* p, const shx_config* cfg_in) {
   cudaMemset(c->m.rec, 0, c->stored_cells * sizeof(CellRec));
   cudaMemset(c->d_stats, 0, ST_COUNT * 8);
   cudaMemset(c->d_flags, 0, 4 * sizeof(int));
+  if (!cfg.no_l2_window && prop.persistingL2CacheMaxSize > 0 &&
+      c->stored_cells * sizeof(int4) <= (size_t)prop.persistingL2CacheMaxSize &&
+      c->stored_cells * sizeof(int4) <= (size_t)prop.accessPolicyMaxWindowSize) {
+    // device-wide carve-out (shared by all contexts of the process on this device)
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize) == cudaSuccess) {
+      c->l2_window.base_ptr = c->m.hq;
+      c->l2_window.num_bytes = c->stored_cells * sizeof(int4);
+      c->l2_window.hitRatio = 1.0f;
+      c->l2_window.hitProp = cudaAccessPropertyPersisting;
+      c->l2_window.missProp = cudaAccessPropertyStreaming;
+      c->l2_window_on = true;
+    } else {
+      cudaGetLastError();
+    }
+  }
   c->peer = peer;
   if (peer) {
     if (cudaMalloc((void**)&c->d_inbox, 3 * kMaxPeers * sizeof(unsigned long long)) != cudaSuccess) {
@@ -388,6 +424,23 @@ int shx_stored_rows(const shx_ctx* c, int* xlo, int* nrows) {
 
 // ------------------------------------------------------------------------------- transfers
 
+// ---- optional per-kernel timing with CUDA events on the context's stream (bench.py's roofline)
+static int span_begin(shx_ctx* c, int kind, cudaStream_t on = nullptr, bool use_on = false) {
+  if (!c->timing) return SHX_OK;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  c->spans.push_back({kind, e0, e1});
+  CU(cudaEventRecord(e0, use_on ? on : c->stream));
+  return SHX_OK;
+}
+static int span_end(shx_ctx* c, cudaStream_t on = nullptr, bool use_on = false) {
+  if (!c->timing) return SHX_OK;
+  CU(cudaEventRecord(c->spans.back().e1, use_on ? on : c->stream));
+  return SHX_OK;
+}
+
+
 static int refresh_halo_ref(shx_ctx* c) {
   for (int side = 0; side < 2; side++) {
     const int rows = side == 0 ? c->halo_lo : c->halo_hi;
@@ -441,31 +494,60 @@ int shx_download_async(shx_ctx* c, shx_cell* pool, size_t ncells, unsigned mask)
   const bool want[8] = {(mask & SHX_F_HEIGHT) != 0, (mask & SHX_F_DISCHARGE) != 0, (mask & SHX_F_MOMENTUM) != 0,
                         (mask & SHX_F_MOMENTUM) != 0, (mask & SHX_F_TRACKS) != 0, (mask & SHX_F_TRACKS) != 0,
                         (mask & SHX_F_TRACKS) != 0, (mask & SHX_F_ROOTDENSITY) != 0};
+  // Two staging tiles and a copy stream: the pack kernel of tile t+1 runs while tile t crosses PCIe.
+  if (!c->copy_stream) {
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      CU(cudaEventCreateWithFlags(&c->ev_packed[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+    }
+    if (cudaMalloc((void**)&c->d_stage2, tile_cells * sizeof(shx_cell)) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(SHX_ERR_NOMEM, "cudaMalloc failed for the second staging tile");
+    }
+  }
+  int turn = 0;
+  bool used[2] = {false, false};
   for (int ti = 0; ti < ms; ti++) {
     const int lx0 = std::max(c->m.row0 - ti * ts, 0), lx1 = std::min(c->m.row1 - ti * ts, ts);
     if (lx0 >= lx1) continue;
     for (int tj = 0; tj < ms; tj++) {
       const size_t node = (size_t)ti * ms + tj;
+      const int b = turn & 1;
+      turn++;
+      shx_cell* stage = b ? c->d_stage2 : c->d_stage;
+      if (used[b]) CU(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));  // the copy that read this buffer is done
       TileArgs a{c->m, sequential(c) ? 1 : 0, ts, ti * ts, tj * ts, c->d_flags};
-      pack_tile_kernel<<<grid_for(c, tile_cells), 256, 0, c->stream>>>(a, c->d_stage);
+      { const int rc_s = span_begin(c, 3); if (rc_s) return rc_s; }
+      pack_tile_kernel<<<grid_for(c, tile_cells), 256, 0, c->stream>>>(a, stage);
+      { const int rc_s = span_end(c); if (rc_s) return rc_s; }
       c->launches++;
+      CU(cudaEventRecord(c->ev_packed[b], c->stream));
+      CU(cudaStreamWaitEvent(c->copy_stream, c->ev_packed[b], 0));
       const size_t first = (size_t)lx0 * ts, count = (size_t)(lx1 - lx0) * ts;
       char* dst = reinterpret_cast<char*>(pool + node * tile_cells + first);
-      const char* src = reinterpret_cast<const char*>(c->d_stage + first);
+      const char* src = reinterpret_cast<const char*>(stage + first);
+      { const int rc_s = span_begin(c, 4, c->copy_stream, true); if (rc_s) return rc_s; }
       if (mask == SHX_F_ALL) {
-        CU(cudaMemcpyAsync(dst, src, count * sizeof(shx_cell), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(dst, src, count * sizeof(shx_cell), cudaMemcpyDeviceToHost, c->copy_stream));
       } else {
         for (int f = 0; f < 8;) {
           if (!want[f]) { f++; continue; }
           int g = f;
           while (g < 8 && want[g]) g++;
           CU(cudaMemcpy2DAsync(dst + 4 * f, sizeof(shx_cell), src + 4 * f, sizeof(shx_cell), (size_t)4 * (g - f), count,
-                               cudaMemcpyDeviceToHost, c->stream));
+                               cudaMemcpyDeviceToHost, c->copy_stream));
           f = g;
         }
       }
+      { const int rc_s = span_end(c, c->copy_stream, true); if (rc_s) return rc_s; }
+      CU(cudaEventRecord(c->ev_copied[b], c->copy_stream));
+      used[b] = true;
     }
   }
+  // stream order for the caller: whatever follows on the context's stream (and shx_sync) sees the copies done
+  for (int b = 0; b < 2; b++)
+    if (used[b]) CU(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
   CU(cudaGetLastError());
   return SHX_OK;
 }
@@ -661,6 +743,30 @@ static int next_claim_epoch(shx_ctx* c) {
   return SHX_OK;
 }
 
+
+// Cooperative launch of a descend kernel.  Where the height / claim words of the context fit the persisting part of
+// L2 (2048^2: 64 MiB of 16-byte cell words), the launch carries an access-policy window over them: the per-call
+// streaming passes (EMA over 32-byte records, vertex fill, view maps) then cannot evict the words every phase of
+// every drop gathers, and the phases of a latency-bound call hit L2 instead of HBM.
+static cudaError_t launch_descend(shx_ctx* c, const void* kernel, int grid, int block, void** args, size_t smem) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.numAttrs = 1;
+  if (c->l2_window_on) {
+    at[1].id = cudaLaunchAttributeAccessPolicyWindow;
+    at[1].val.accessPolicyWindow = c->l2_window;
+    cfg.numAttrs = 2;
+  }
+  cfg.attrs = at;
+  return cudaLaunchKernelExC(&cfg, kernel, args);
+}
+
 // march n drops already in c->d_drops
 static int run_device_drops(shx_ctx* c, size_t n, bool trace, bool align_age = false) {
   c->last_n = n;
@@ -695,7 +801,7 @@ static int run_device_drops(shx_ctx* c, size_t n, bool trace, bool align_age = f
     c->launches++;
     void* args[] = {&a};
     const int grid = (int)std::max<size_t>(1, (n + ls.block - 1) / ls.block);
-    CU(cudaLaunchCooperativeKernel(ls.kernel, dim3(grid), dim3(ls.block), args, ls.smem(ls.block), c->stream));
+    CU(launch_descend(c, ls.kernel, grid, ls.block, args, ls.smem(ls.block)));
     c->launches++;
     return SHX_OK;
   }
@@ -742,7 +848,7 @@ static int run_device_drops(shx_ctx* c, size_t n, bool trace, bool align_age = f
       take = left;
       a.ndrops = (unsigned)take;
       const int block = (int)((take * 8 + 31) / 32 * 32);
-      CU(cudaLaunchCooperativeKernel((void*)KERNEL_SMALL, dim3(1), dim3(block), args, (size_t)kGroupSmemWords * 4 * block, c->stream));
+      CU(launch_descend(c, (const void*)KERNEL_SMALL, 1, block, args, (size_t)kGroupSmemWords * 4 * block));
     } else {
       // eight lanes per drop while the whole batch is co-resident that way, one thread per drop beyond
       const LaunchShape& g = c->shape[0];
@@ -755,7 +861,7 @@ static int run_device_drops(shx_ctx* c, size_t n, bool trace, bool align_age = f
       take = std::min(left, (size_t)cap * per_block);
       a.ndrops = (unsigned)take;
       const int grid = (int)((take + per_block - 1) / per_block);
-      CU(cudaLaunchCooperativeKernel(ls.kernel, dim3(grid), dim3(block), args, ls.smem(block), c->stream));
+      CU(launch_descend(c, ls.kernel, grid, block, args, ls.smem(block)));
     }
     c->launches++;
     done += take;
@@ -789,22 +895,6 @@ static int spawn_device(shx_ctx* c, int cycles, uint64_t seed, uint64_t epoch, s
   return SHX_OK;
 }
 
-// ---- optional per-kernel timing with CUDA events on the context's stream (bench.py's roofline)
-static int span_begin(shx_ctx* c, int kind) {
-  if (!c->timing) return SHX_OK;
-  cudaEvent_t e0, e1;
-  CU(cudaEventCreate(&e0));
-  CU(cudaEventCreate(&e1));
-  c->spans.push_back({kind, e0, e1});
-  CU(cudaEventRecord(e0, c->stream));
-  return SHX_OK;
-}
-static int span_end(shx_ctx* c) {
-  if (!c->timing) return SHX_OK;
-  CU(cudaEventRecord(c->spans.back().e1, c->stream));
-  return SHX_OK;
-}
-
 int shx_timing_enable(shx_ctx* c, int on) {
   if (!c) return fail(SHX_ERR_ARG, "null context");
   c->timing = on != 0;
@@ -821,7 +911,10 @@ int shx_timing_read(shx_ctx* c, shx_timing* out) {
     CU(cudaEventElapsedTime(&ms, s.e0, s.e1));
     if (s.kind == 0) out->spawn_ms += ms;
     else if (s.kind == 1) { out->descend_ms += ms; out->descend_launches++; }
-    else out->ema_ms += ms;
+    else if (s.kind == 2) out->ema_ms += ms;
+    else if (s.kind == 3) out->pack_ms += ms;
+    else if (s.kind == 4) out->d2h_ms += ms;
+    else out->push_ms += ms;
     cudaEventDestroy(s.e0);
     cudaEventDestroy(s.e1);
   }
@@ -940,20 +1033,35 @@ static int push_rootdensity(shx_ctx* c, const int* xy, const float* delta, size_
   if (!c || ((!xy || !delta) && n)) return fail(SHX_ERR_ARG, "null argument");
   if (!n) return SHX_OK;
   CU(cudaSetDevice(c->cfg.device));
-  int* d_xy = nullptr;
-  float* d_delta = nullptr;
-  CU(cudaMallocAsync((void**)&d_xy, n * 2 * sizeof(int), c->stream));
-  CU(cudaMallocAsync((void**)&d_delta, n * sizeof(float), c->stream));
-  CU(cudaMemcpyAsync(d_xy, xy, n * 2 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(d_delta, delta, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  if (absolute) set_rootdensity_kernel<<<grid_for(c, n), 256, 0, c->stream>>>(c->m, d_xy, d_delta, n);
-  else add_rootdensity_kernel<<<1, 1, 0, c->stream>>>(c->m, d_xy, d_delta, n);
+  const size_t b_xy = n * 2 * sizeof(int), b_val = n * sizeof(float);
+  if (c->push_cap < b_xy + b_val) {  // grow-only buffers
+    if (c->push_done) CU(cudaEventSynchronize(c->push_done));
+    cudaFree(c->d_push);
+    if (c->h_push) cudaFreeHost(c->h_push);
+    c->d_push = c->h_push = nullptr;
+    c->push_cap = 0;
+    const size_t cap = std::max<size_t>(2 * (b_xy + b_val), 1 << 16);
+    if (cudaMalloc((void**)&c->d_push, cap) != cudaSuccess || cudaMallocHost((void**)&c->h_push, cap) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(SHX_ERR_NOMEM, "allocation of the rootdensity push buffers failed");
+    }
+    c->push_cap = cap;
+    if (!c->push_done) CU(cudaEventCreateWithFlags(&c->push_done, cudaEventDisableTiming));
+  } else {
+    CU(cudaEventSynchronize(c->push_done));  // the previous push has left the bounce buffer
+  }
+  memcpy(c->h_push, xy, b_xy);  // the caller's arrays are free again when this call returns
+  memcpy(c->h_push + b_xy, delta, b_val);
+  { const int rc_s = span_begin(c, 5); if (rc_s) return rc_s; }
+  CU(cudaMemcpyAsync(c->d_push, c->h_push, b_xy + b_val, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaEventRecord(c->push_done, c->stream));
+  const int* d_xy = reinterpret_cast<const int*>(c->d_push);
+  const float* d_val = reinterpret_cast<const float*>(c->d_push + b_xy);
+  if (absolute) set_rootdensity_kernel<<<grid_for(c, n), 256, 0, c->stream>>>(c->m, d_xy, d_val, n);
+  else add_rootdensity_kernel<<<1, 1, 0, c->stream>>>(c->m, d_xy, d_val, n);
   c->launches++;
   CU(cudaGetLastError());
-  CU(cudaFreeAsync(d_xy, c->stream));
-  CU(cudaFreeAsync(d_delta, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  return SHX_OK;
+  return span_end(c);  // stream-ordered: the next erode / download on this context sees the values
 }
 
 int shx_synth_terrain(shx_ctx* c, uint32_t seed) {

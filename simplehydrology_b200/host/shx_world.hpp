@@ -7,7 +7,7 @@
 //
 //   shx::Bridge bridge(cellpool.root.start, quad::mapsize, quad::tilesize);   // after World::map.init
 //   ...
-//   bridge.erode<Drop, World>(quad::tilesize);   // instead of world.erode(quad::tilesize)
+//   bridge.erode<Drop, World>(quad::tilesize, &Vegetation::plants);   // instead of world.erode(quad::tilesize)
 //   Vegetation::grow();                          // unchanged, edits rootdensity in the host pool
 //   updatenode(...);                             // unchanged, reads height from the host pool
 //
@@ -44,78 +44,157 @@ inline void params_from_statics(shx_params& p) {
 class Bridge {
  public:
   // `pool` is the reference's tiled AoS cell pool (quad::cell == shx_cell, 32 bytes); it stays owned
-  // by the caller and must outlive the bridge.
-  Bridge(void* pool, int mapsize, int tilesize, int device = 0, bool pin_host_pool = true)
-      : pool_(static_cast<shx_cell*>(pool)) {
+  // by the caller and must outlive the bridge.  ngpu > 1 spreads the map over that many GPUs as row strips
+  // (shx_multi: one host thread, peer stores over NVLink once per call; mapsize must be divisible by ngpu).
+  // shadow_roots: keep a copy of the pool's rootdensity so that the erode overloads WITHOUT a plant list can find
+  // what the host changed (4 bytes per cell and one pass per frame); pass false when every call hands over the plants.
+  Bridge(void* pool, int mapsize, int tilesize, int ngpu = 1, const int* devices = nullptr, bool pin_host_pool = true,
+         bool shadow_roots = true)
+      : pool_(static_cast<shx_cell*>(pool)), shadow_roots_(shadow_roots) {
     static_assert(sizeof(shx_cell) == 32, "quad::cell layout (cellpool.h:207-220)");
     shx_default_params(&params_, mapsize);
     params_.tilesize = tilesize;
     ncells_ = (size_t)mapsize * mapsize * (size_t)tilesize * tilesize;
-    shx_config cfg;
-    shx_default_config(&cfg);
-    cfg.device = device;
-    check(shx_create(&ctx_, &params_, &cfg), "shx_create");
+    if (shx_multi_create(&multi_, &params_, ngpu, devices, nullptr) != SHX_OK)
+      throw std::runtime_error(std::string("shx_multi_create: ") + shx_multi_last_error());
     if (pin_host_pool && shx_host_register(pool_, ncells_ * sizeof(shx_cell)) == SHX_OK) pinned_ = true;
-    check(shx_upload(ctx_, pool_, ncells_), "shx_upload");
-    root_shadow_.resize(ncells_);
-    for (size_t i = 0; i < ncells_; i++) root_shadow_[i] = pool_[i].rootdensity;
+    mcheck(shx_multi_upload(multi_, pool_, ncells_), "shx_multi_upload");
+    snapshot_roots();
   }
   ~Bridge() {
+    shx_multi_destroy(multi_);
     if (pinned_) shx_host_unregister(pool_);
-    shx_destroy(ctx_);
   }
   Bridge(const Bridge&) = delete;
   Bridge& operator=(const Bridge&) = delete;
 
-  // == World::erode(cycles) with the statics of the given Drop / World types
+  // == World::erode(cycles) with the statics of the given Drop / World types.
+  // `plants` (optional): the reference's Vegetation::plants (vegetation.h:48-53), or any container of objects with
+  // a `pos` of two floats.  Plant::root (vegetation.h:87-118) writes rootdensity straight into the host pool, always
+  // into the 3x3 cells around a plant; with the plant list the bridge pushes exactly those cells (of the plants
+  // alive now and of those alive at the previous call: a plant that died was un-rooted first) instead of scanning
+  // the whole pool for changes -- 36 000 cells instead of 67 million at 8192^2.  Without it the whole pool is
+  // compared with a shadow copy (any writer is caught; O(cells) per frame).
+  template <class DropT, class WorldT, class PlantVec>
+  shx_stats erode(int cycles, const PlantVec* plants) {
+    params_from_statics<DropT, WorldT>(params_);
+    push_roots_near(*plants);
+    return run(cycles, params_, (uint64_t)WorldT::SEED);
+  }
   template <class DropT, class WorldT>
   shx_stats erode(int cycles) {
     params_from_statics<DropT, WorldT>(params_);
-    return erode(cycles, params_, (uint64_t)WorldT::SEED);
+    push_roots_by_scan();
+    return run(cycles, params_, (uint64_t)WorldT::SEED);
   }
-
   shx_stats erode(int cycles, const shx_params& p, uint64_t seed) {
-    params_ = p;
-    check(shx_set_params(ctx_, &params_), "shx_set_params");
-    push_rootdensity();
-    shx_stats st;
-    check(shx_erode(ctx_, cycles, seed, &st), "shx_erode");
-    // Whole records: one contiguous DMA per tile.  (Selecting height/discharge/momentum only makes it a
-    // strided 16-of-32-byte copy, measured 2x SLOWER at 8192^2.)  rootdensity comes back as pushed above;
-    // the *_track fields are scratch of the erode call (world.h:56-61 zeroes them first thing).
-    check(shx_download(ctx_, pool_, ncells_, SHX_F_ALL), "shx_download");
-    return st;
+    push_roots_by_scan();
+    return run(cycles, p, seed);
   }
 
   // the host edited heights or fields wholesale (e.g. regenerated the world): send everything again
   void reupload() {
-    check(shx_upload(ctx_, pool_, ncells_), "shx_upload");
-    for (size_t i = 0; i < ncells_; i++) root_shadow_[i] = pool_[i].rootdensity;
+    mcheck(shx_multi_upload(multi_, pool_, ncells_), "shx_multi_upload");
+    snapshot_roots();
   }
 
   // == `for (auto& node : world.map.nodes) updatenode(vertexpool, node);` (SimpleHydrology.cpp:322-324)
   // on the device.  `vertices` receives the 48-byte Vertex records (vertexpool.h:6-26) of every
   // cell in pool order, i.e. exactly what the reference's Vertexpool<Vertex>::fill calls leave in
-  // the pool's mapped buffer (sections are reserved node by node, cellpool.h:327-336).
-  void update_vertices(float* vertices) { check(shx_vertex_download(ctx_, vertices, ncells_), "shx_vertex_download"); }
-  // the same straight into device memory, e.g. the vertex pool's VBO registered with
-  // cudaGraphicsGLRegisterBuffer and mapped: no vertex data crosses PCIe
-  void update_vertices_device(float* dev_vertices) { check(shx_vertex_fill(ctx_, dev_vertices), "shx_vertex_fill"); }
+  // the pool's mapped buffer (sections are reserved node by node, cellpool.h:327-336).  Strips are whole tile rows,
+  // so strip i's records are a contiguous slice of the pool order.
+  void update_vertices(float* vertices) {
+    size_t off = 0;
+    for (int i = 0; i < shx_multi_strips(multi_); i++) {
+      const size_t n = ncells_ / (size_t)shx_multi_strips(multi_);
+      check(shx_vertex_download(shx_multi_strip(multi_, i), vertices + 12 * off, n), "shx_vertex_download");
+      off += n;
+    }
+  }
+  // the same straight into device memory of the (single) GPU, e.g. the vertex pool's VBO registered with
+  // cudaGraphicsGLRegisterBuffer and mapped (see shx_gl.hpp): no vertex data crosses PCIe
+  void update_vertices_device(float* dev_vertices) { check(shx_vertex_fill(context(), dev_vertices), "shx_vertex_fill"); }
   // == the dischargeMap / momentumMap lambdas (SimpleHydrology.cpp:341-354): 4 floats per cell in
   // map order {erf(0.4*discharge), 0.5*(1+erf(momentumx)), 0.5*(1+erf(momentumy)), height}
-  void view_maps(float* rgba) { check(shx_view_maps_download(ctx_, rgba, ncells_), "shx_view_maps_download"); }
-
-  // sparse read-back instead of the pool download: the records (and World::map.normal) of n cells {x, y}
-  void gather(const int* xy, size_t n, shx_cell* out, float* normals3 = nullptr) {
-    check(shx_gather_cells(ctx_, xy, n, out, normals3), "shx_gather_cells");
+  void view_maps(float* rgba) {
+    size_t off = 0;
+    for (int i = 0; i < shx_multi_strips(multi_); i++) {
+      const size_t n = ncells_ / (size_t)shx_multi_strips(multi_);
+      check(shx_view_maps_download(shx_multi_strip(multi_, i), rgba + 4 * off, n), "shx_view_maps_download");
+      off += n;
+    }
   }
 
-  shx_ctx* context() { return ctx_; }
+  // sparse read-back instead of the pool download (single GPU): the records (and World::map.normal) of n cells {x, y}
+  void gather(const int* xy, size_t n, shx_cell* out, float* normals3 = nullptr) {
+    check(shx_gather_cells(context(), xy, n, out, normals3), "shx_gather_cells");
+  }
+
+  shx_ctx* context() { return shx_multi_strip(multi_, 0); }  // the first (or only) strip
+  shx_multi* multi() { return multi_; }
   const shx_params& params() const { return params_; }
+  size_t last_push() const { return val_.size(); }  // rootdensity cells sent by the last erode call
 
  private:
-  // Plant::root (vegetation.h:87-118) writes rootdensity straight into the pool; find what moved
-  void push_rootdensity() {
+  static void mcheck(int rc, const char* what) {
+    if (rc != SHX_OK) throw std::runtime_error(std::string(what) + ": " + shx_multi_last_error());
+  }
+
+  shx_stats run(int cycles, const shx_params& p, uint64_t seed) {
+    params_ = p;
+    mcheck(shx_multi_set_params(multi_, &params_), "shx_multi_set_params");
+    if (!val_.empty()) mcheck(shx_multi_set_rootdensity(multi_, xy_.data(), val_.data(), val_.size()), "shx_multi_set_rootdensity");
+    shx_stats st;
+    mcheck(shx_multi_erode(multi_, cycles, seed, &st), "shx_multi_erode");
+    // Whole records: one contiguous DMA per tile.  (Selecting height/discharge/momentum only makes it a
+    // strided 16-of-32-byte copy, measured 2x SLOWER at 8192^2.)  rootdensity comes back as pushed above;
+    // the *_track fields are scratch of the erode call (world.h:56-61 zeroes them first thing).
+    mcheck(shx_multi_download(multi_, pool_, ncells_, SHX_F_ALL), "shx_multi_download");
+    return st;
+  }
+
+  size_t pool_index(int x, int y) const {  // cellpool.h:327-336, math.h:11-14
+    const int ts = params_.tilesize;
+    return ((size_t)(x / ts) * params_.mapsize + (size_t)(y / ts)) * ts * ts + (size_t)(x % ts) * ts + (size_t)(y % ts);
+  }
+
+  // the 3x3 cells around every plant of this and of the previous call (Plant::root, vegetation.h:87-118)
+  template <class PlantVec>
+  void push_roots_near(const PlantVec& plants) {
+    const int size = params_.mapsize * params_.tilesize;
+    std::vector<int> now;
+    now.reserve(plants.size() * 2);
+    for (const auto& pl : plants) {
+      now.push_back((int)pl.pos.x);
+      now.push_back((int)pl.pos.y);
+    }
+    xy_.clear();
+    val_.clear();
+    auto add = [&](const std::vector<int>& at) {
+      for (size_t k = 0; k + 1 < at.size(); k += 2)
+        for (int dx = -1; dx <= 1; dx++)
+          for (int dy = -1; dy <= 1; dy++) {
+            const int x = at[k] + dx, y = at[k + 1] + dy;
+            if (x < 0 || y < 0 || x >= size || y >= size) continue;  // getCell() == NULL
+            xy_.push_back(x);
+            xy_.push_back(y);
+            val_.push_back(pool_[pool_index(x, y)].rootdensity);
+          }
+    };
+    add(prev_plants_);  // first, so that a cell listed twice ends with the same (current) value either way
+    add(now);
+    prev_plants_.swap(now);
+  }
+
+  void snapshot_roots() {
+    if (!shadow_roots_) return;
+    root_shadow_.resize(ncells_);
+    for (size_t i = 0; i < ncells_; i++) root_shadow_[i] = pool_[i].rootdensity;
+  }
+
+  // any writer: compare the whole pool with the shadow copy
+  void push_roots_by_scan() {
+    if (!shadow_roots_) throw std::runtime_error("shx::Bridge: erode without a plant list needs shadow_roots = true");
     xy_.clear();
     val_.clear();
     const int ts = params_.tilesize, ms = params_.mapsize;
@@ -124,20 +203,21 @@ class Bridge {
       const float r = pool_[i].rootdensity;
       if (std::memcmp(&r, &root_shadow_[i], sizeof r) == 0) continue;
       root_shadow_[i] = r;
-      const size_t node = i / tile, in = i % tile;  // cellpool.h:327-336, math.h:11-14
+      const size_t node = i / tile, in = i % tile;
       xy_.push_back((int)(node / ms) * ts + (int)(in / ts));
       xy_.push_back((int)(node % ms) * ts + (int)(in % ts));
       val_.push_back(r);
     }
-    if (!val_.empty()) check(shx_set_rootdensity(ctx_, xy_.data(), val_.data(), val_.size()), "shx_set_rootdensity");
   }
 
   shx_cell* pool_;
   size_t ncells_ = 0;
-  shx_ctx* ctx_ = nullptr;
+  shx_multi* multi_ = nullptr;
   shx_params params_;
   bool pinned_ = false;
+  bool shadow_roots_ = true;
   std::vector<float> root_shadow_;
+  std::vector<int> prev_plants_;
   std::vector<int> xy_;
   std::vector<float> val_;
 };
