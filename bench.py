@@ -4,15 +4,19 @@
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
   python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU loop (oracle/_ref)
 
-One "step" = one erosion cycle = one World::erode(512)-equivalent (reset + 512 drops per 512^2 node +
-EMA, what one reference frame does: SimpleHydrology.cpp:319) on the 8192x8192 configuration of
-BASELINE.json (configs[3], the one quoted at 1/2/4/8 GPUs; it fits one GPU), synthetic seeded
-terrain.  N > 1 partitions the same map into row strips, one process per GPU (strong scaling).
-Metric: particle steps/s (one particle step = one Drop::descend call); cycles/s rides along.
+One "step" = one erosion cycle = one World::erode(512) call (reset + 512 drops per 512^2 node + EMA, what one
+reference frame does: SimpleHydrology.cpp:319) on the 8192x8192 configuration of BASELINE.json (configs[3], the one
+quoted at 1/2/4/8 GPUs; it fits one GPU), on the reference's OWN terrain: World::map.init with SEED 1
+(cellpool.h:349-409), generated on the device by shx_init_terrain (bit-identical to the host init).  N > 1 partitions
+the same map into row strips, one process per GPU (strong scaling).  Metric: particle steps/s (one particle step = one
+Drop::descend call); cycles/s rides along.  Both arms run the same job: the reference arm marches the whole
+131 072-drop cycle through the reference's own Drop::descend / World::cascade on one host thread (all it can use).
 
-Rank 0 prints ONE JSON line.  `value` is timed with the world resident in HBM; `e2e` goes through
-the C-ABI calls the host adaptor makes, with host buffers: per step a rootdensity push from pinned
-host memory, shx_erode, and the download of the cell records into the host cell pool.
+Rank 0 prints ONE JSON line.  `value` is timed with the world resident in HBM; `e2e` is the C++ host adaptor's
+frame (simplehydrology_b200/host/bench_bridge.cpp: shx::Bridge::erode on a HOST cell pool: sparse rootdensity push,
+erode, download of the 32-byte records), with a per-call breakdown.  `configs` adds the reference's own map sizes
+(512^2, 2048^2: latency regime, set against a measured L2 bandwidth), `mature_world` the same 8192^2 cycle after 200
+calls, `roofline.traffic` the DRAM bytes of one descend launch measured by an ncu child process of this run.
 """
 import argparse
 import json
@@ -86,30 +90,57 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+# ------------------------------------------------------------------------------ the job both arms run
+
+def workload_config():
+    """the workload, identically worded in both arms' JSON lines"""
+    return {"workload": "8192x8192 world (mapsize 16, BASELINE configs[3]) on the reference's own terrain (World::map.init, SEED 1); "
+                        "one step = one World::erode(512) call: reset, 131072 drops (512 per 512^2 node) marched to the end, EMA",
+            "map": "8192x8192", "terrain": "World::map.init(SEED=1), cellpool.h:349-409", "drops_per_cycle": MAPSIZE * MAPSIZE * CYCLES,
+            "cycles_per_step": 1, "seed": SEED,
+            "l2": "inputs larger than L2 (3.2 GB of map state vs 126 MB): no flush needed"}
+
+
+def node_major_spawns(rng, mapsize, cycles):
+    """world.h:64-69: for every node, `cycles` positions node.pos + (rand % 512, rand % 512), node-major"""
+    import numpy as np
+    nodes = np.arange(mapsize * mapsize)
+    ox = np.repeat((nodes // mapsize) * 512, cycles)
+    oy = np.repeat((nodes % mapsize) * 512, cycles)
+    xy = rng.integers(0, 512, size=(mapsize * mapsize * cycles, 2))
+    xy[:, 0] += ox
+    xy[:, 1] += oy
+    return xy.astype(np.float32)
+
+
 # ------------------------------------------------------------------------------ reference arm
 
-def reference_world(mapsize, seed):
-    """the reference's own World (oracle/_ref, mapsize variant) holding the synthetic terrain"""
+def reference_world(mapsize, seed, heights=None):
+    """the reference's own World (oracle/_ref, mapsize variant) holding the map::init terrain.  The terrain comes
+    from `heights` (tiled pool order) or from the oracle's restatement of map::init (OpenMP over the host cores;
+    the reference's own single-threaded init takes minutes at 8192^2) -- bit-identical either way."""
     import ctypes as C
     import orc
     if not orc.have_ref(mapsize):
         return None
     R = orc.Ref(mapsize)  # blank world: node table as cellpool.h:327-336, heights filled below
-    p = orc.default_params(mapsize)
-    h = orc.synth_terrain(512 * mapsize, seed)
-    orc.lib().orc_fill_tiled_from_planar(C.byref(p), h.ctypes.data, R.cells.ctypes.data)
+    if heights is not None:
+        R.cells["height"] = heights
+    else:
+        p = orc.default_params(mapsize)
+        h = orc.init_terrain(mapsize, seed)
+        orc.lib().orc_fill_tiled_from_planar(C.byref(p), h.ctypes.data, R.cells.ctypes.data)
     return R
 
 
-def time_reference(R, mapsize, drops_per_step, steps, warmup, seed=SEED):
-    """World::erode's loop with explicit spawns (reset, spawn + `while(drop.descend())` per drop, EMA)
-    over the reference's own Drop::descend / World::cascade; (particle steps, seconds) of `steps` samples"""
+def time_reference(R, mapsize, cycles, steps, warmup, seed=SEED):
+    """World::erode's loop with explicit spawns (reset, spawn + `while(drop.descend())` per drop, EMA) over the
+    reference's own Drop::descend / World::cascade; (particle steps, seconds) of `steps` whole calls"""
     import numpy as np
     rng = np.random.default_rng(seed)
-    size = 512 * mapsize
     total_steps, total_s = 0, 0.0
     for i in range(warmup + steps):
-        xy = rng.integers(0, size, size=(drops_per_step, 2)).astype(np.float32)
+        xy = node_major_spawns(rng, mapsize, cycles)
         t0 = time.perf_counter()
         st = R.erode_spawnlist(xy)
         dt = time.perf_counter() - t0
@@ -122,7 +153,8 @@ def time_reference(R, mapsize, drops_per_step, steps, warmup, seed=SEED):
 def replica_worker(seconds, seed):
     """one independent reference world (2048^2, its own seed) eroding for ~`seconds`; prints its particle steps and time"""
     import numpy as np
-    R = reference_world(4, seed)
+    import orc
+    R = reference_world(4, seed, heights=orc.planar_to_tiled(orc.default_params(4), orc.synth_terrain(2048, seed))["height"])
     if R is None:
         print("0 1.0")
         return 0
@@ -151,24 +183,24 @@ def reference_replicas(ncores, seconds=6.0):
 
 
 def run_reference(args):
+    """the same job on the reference's own CPU implementation: K whole erode(512) calls at 8192^2 after W warm-up
+    calls, one host thread (the loop is sequential and non-reentrant: world.h:111 static scratch, global rand())"""
     if int(os.environ.get("RANK", "0")) != 0:
         return 0
     R = reference_world(MAPSIZE, SEED)
     if R is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libshx_ref_m16.so missing (run __graft_entry__.build() where /root/reference exists)"}))
         return 0
-    drops = 4096  # bounded sample of one cycle's 131072 drops: ~2 s of CPU per step incl. the full reset+EMA passes
-    warm = min(args.warmup, 1)
-    nsteps, secs = time_reference(R, MAPSIZE, drops, args.steps, warm)
+    nsteps, secs = time_reference(R, MAPSIZE, CYCLES, args.steps, args.warmup)
     value = nsteps / secs
-    sample = (f"{drops} of the cycle's {MAPSIZE * MAPSIZE * CYCLES} drops per step on the same 8192^2 synthetic world, "
-              "incl. the reset and EMA passes over all cells")
+    sample = (f"{args.steps} whole erode(512) calls ({MAPSIZE * MAPSIZE * CYCLES} drops each) after {args.warmup} warm-up calls, through the "
+              "reference's own Drop::descend / World::cascade (oracle/_ref, its headers compiled unmodified), incl. the reset and EMA passes")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": warm, "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "8192x8192 world (mapsize 16), erode(512)-equivalent cycle, reference CPU loop", "map": "8192x8192",
-                       "drops_per_step": drops, "threads": 1,
-                       "note": "the reference loop is sequential and non-reentrant (world.h:111 static scratch, global rand): 1 thread is all it can use"},
+            "config": workload_config(),
+            "parallelism": "1 host thread: the reference loop is sequential and non-reentrant (world.h:111 static scratch, global rand())",
+            "cycles_per_s": args.steps / secs,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "host_cores": os.cpu_count()}
@@ -178,7 +210,91 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------ CUDA arm
 
+def timed_calls(W, cycles, calls, warm, seed=SEED):
+    """`calls` erode(cycles) calls on a resident world between CUDA events; (ms per call, summed stats of the timed calls)"""
+    import torch
+    for _ in range(warm):
+        W.erode_async(cycles, seed)
+    W.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    acc = {}
+    e0.record()
+    for _ in range(calls):
+        W.erode_async(cycles, seed)
+        st = W.read_stats()
+        for n, _t in st._fields_:
+            acc[n] = acc.get(n, 0) + int(getattr(st, n))
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / calls, acc
+
+
+def small_config(shx, torch, mapsize, cycles, calls, warm, l2_gbs):
+    """the reference's own map sizes (BASELINE configs[1], [2]): latency regime, map state mostly L2-resident"""
+    with shx.World(mapsize=mapsize) as W:
+        W.set_stream(torch.cuda.current_stream().cuda_stream)
+        W.init_terrain(SEED)
+        ms, acc = timed_calls(W, cycles, calls, warm)
+    steps = acc["steps"] / calls
+    achieved = steps * BYTES_PER_STEP / (ms * 1e-3) / 1e9
+    side = 512 * mapsize
+    return {"map": f"{side}x{side}", "call": f"erode({cycles})", "drops_per_call": mapsize * mapsize * cycles, "calls_timed": calls,
+            "ms_per_call": ms, "calls_per_s": 1e3 / ms, "particle_steps_per_s": steps / (ms * 1e-3),
+            "phases_per_call": acc["phases"] / calls, "us_per_phase": 1e3 * ms / max(acc["phases"] / calls, 1),
+            "mean_steps_per_drop": acc["steps"] / max(acc["spawned"], 1),
+            "map_state_mb": side * side * 48 / 1e6,
+            "roofline": {"bound": "l2", "achieved": achieved, "peak": l2_gbs, "unit": "GB/s", "frac": achieved / l2_gbs if l2_gbs else None,
+                         "note": "algorithmic 88 B per particle step against the measured L2 read bandwidth (l2_peak below); the regime is "
+                                 "bound by the per-phase latency chain, not by bandwidth"}}
+
+
+def measure_traffic():
+    """DRAM bytes of ONE descend launch of this workload, measured now by an ncu child process (never a timed number)"""
+    ncu = next((c for c in ("/usr/local/cuda/bin/ncu", "ncu") if os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)), "ncu")
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum", "--clock-control", "none",
+           "-k", "regex:descend_lockstep", "-s", "2", "-c", "1", "--csv", sys.executable, os.path.abspath(__file__), "--traffic-probe"]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=240).stdout
+        import csv
+        rows = [r for r in csv.reader(out.splitlines()) if len(r) > 10]
+        hdr = rows[0]
+        vals = {}
+        for r in rows[1:]:
+            d = dict(zip(hdr, r))
+            v = float(d["Metric Value"].replace(",", ""))
+            unit = d["Metric Unit"].lower()
+            scale = {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12}.get(unit, 1.0)
+            vals[d["Metric Name"]] = v * scale
+        return vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"], "measured by this run: ncu child process, one descend launch of the same workload"
+    except Exception as e:  # no ncu on the box, or it failed: say so rather than quote an old number
+        return None, f"unavailable ({type(e).__name__}: {e})"
+
+
+def traffic_probe():
+    import torch
+    import simplehydrology_b200 as shx
+    with shx.World(mapsize=MAPSIZE) as W:
+        W.init_terrain(SEED)
+        for _ in range(4):
+            W.erode(CYCLES, SEED)
+    return 0
+
+
+def run_bridge(ngpu, frames=5, warmup=1):
+    """the C++ host adaptor's own frame loop on a host pool (simplehydrology_b200/host/bench_bridge.cpp)"""
+    exe = os.path.join(ROOT, "simplehydrology_b200", "host", "bench_bridge")
+    if not os.path.exists(exe):
+        from simplehydrology_b200 import build as B
+        B.build()
+        B.build_host_example()
+    r = subprocess.run([exe, str(MAPSIZE), str(frames), str(warmup), str(ngpu), str(SEED)], capture_output=True, text=True, timeout=600)
+    if r.returncode != 0:
+        raise RuntimeError(f"bench_bridge failed: {r.stderr.strip()[-400:]}")
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
 def run_cuda(args):
+    import datetime
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -203,7 +319,7 @@ def run_cuda(args):
         strip = strips.GpuStrip(MAPSIZE, rank, world, local)
         ex = strips.StripExchange(strip, rank, world)
     W = strip.W
-    W.synth_terrain(SEED)
+    W.init_terrain(SEED)  # the reference's own terrain, every strip its rows (+ halo)
     names = [n for n, _ in shx.Stats._fields_]
 
     def barrier():
@@ -273,28 +389,23 @@ def run_cuda(args):
         achieved = rank_steps * BYTES_PER_STEP / (descend_ms * 1e-3) / 1e9 if descend_ms > 0 else 0.0
         ema_ms = tm.ema_ms / max(args.steps, 1)
         ema_gbs = (cells / world) * BYTES_PER_CELL_EMA / (ema_ms * 1e-3) / 1e9 if ema_ms > 0 else 0.0
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "descend_traffic.json")
-        if os.path.exists(tpath):
-            with open(tpath) as fh:
-                traffic = json.load(fh).get("dram_bytes_per_launch")
+        cfg = workload_config()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic",
-                "config": {"workload": "8192x8192 world (mapsize 16, BASELINE configs[3]); one step = one erode(512) cycle: 131072 drops, "
-                                       "lock-step batched descend + cascade, EMA",
-                           "map": "8192x8192", "drops_per_cycle": MAPSIZE * MAPSIZE * CYCLES,
-                           "parallelism": {"peer": f"row strips x{world}, peer-mapped over NVLink, one cross-GPU barrier per phase (bit-identical to 1 GPU)",
-                                            "cycle": f"row strips x{world}, halo rows and border-crossing drops exchanged once per cycle (NCCL send/recv)",
-                                            "rounds": f"row strips x{world}, exchange rounds until no drop is in flight"}[args.multi] if world > 1 else "single GPU",
-                           "l2": "inputs larger than L2 (2.7 GB of map state vs 126 MB): no flush needed", "seed": SEED},
+                "data": "synthetic", "config": cfg,
+                "parallelism": {"peer": f"row strips x{world}, peer-mapped over NVLink, one cross-GPU barrier per phase (bit-identical to 1 GPU)",
+                                "cycle": f"row strips x{world}, one process per GPU, halo rows and border-crossing drops exchanged once per cycle (NCCL send/recv)",
+                                "rounds": f"row strips x{world}, exchange rounds until no drop is in flight"}[args.multi] if world > 1 else "single GPU",
                 "cycles_per_s": args.steps / (ms * 1e-3),
                 "mean_steps_per_drop": psteps / max(total["spawned"], 1),
+                "phases_per_cycle": acc["phases"] / max(args.steps, 1),
                 "cascade_transfers_per_step": total["cascade_transfers"] / max(psteps, 1),
                 "gpu_launches": total["launches"],
-                "roofline": {"bound": "hbm", "kernel": "descend_lockstep_kernel", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                             "frac": achieved / hbm, "traffic": traffic, "peak_source": peak_src,
+                "roofline": {"bound": "hbm", "kernel": "descend_lockstep_kernel" if rank_steps / 490 > 18944 else "descend_group_kernel",
+                             "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                             "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
                              "algorithmic_bytes_per_particle_step": BYTES_PER_STEP, "kernel_ms_per_cycle": descend_ms,
+                             "us_per_phase": 1e3 * descend_ms / max(acc["phases"] / max(args.steps, 1), 1),
                              "share_of_step": descend_ms / (ms / args.steps),
                              "ema_kernel": {"achieved": ema_gbs, "frac": ema_gbs / hbm, "ms_per_launch": ema_ms,
                                             "algorithmic_bytes_per_cell": BYTES_PER_CELL_EMA}},
@@ -310,9 +421,10 @@ def run_cuda(args):
     # kernels on the resident world: vertex fill (updatenode) and the discharge / momentum maps
     own = (strip.row1 - strip.row0) * 512 * MAPSIZE
     views = {}
-    for name, words, nbytes in (("vertex_fill", 12, 52), ("view_maps", 4, 36)):
+    for name, words, nbytes in (("vertex_fill", 12, 52), ("view_maps", 4, 36), ("view_textures", 2, 20)):
         buf = torch.empty(own * words, dtype=torch.float32, device=dev)
-        fn = (lambda: W.vertex_fill(buf.data_ptr())) if name == "vertex_fill" else (lambda: W.view_maps(buf.data_ptr()))
+        fn = {"vertex_fill": lambda: W.vertex_fill(buf.data_ptr()), "view_maps": lambda: W.view_maps(buf.data_ptr()),
+              "view_textures": lambda: W.view_textures(buf.data_ptr(), buf.data_ptr() + 4 * own)}[name]
         for _ in range(3):
             fn()
         v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -328,96 +440,99 @@ def run_cuda(args):
     if rank == 0:
         line["roofline"]["view_kernels"] = views
 
-    # ---- e2e: the calls the host adaptor makes, with host buffers; with strips every rank downloads
-    # its own rows into its own (whole-map sized, as the reference's) pool
-    # pinned host memory (cudaHostAlloc through torch; registering a pageable numpy buffer can fail silently under a
-    # low RLIMIT_MEMLOCK, which turns the 2-GiB download into a pageable copy at a quarter of the speed)
-    pool_t = torch.empty(cells * shx.CELL_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
-    pool_t.zero_()
-    pool = pool_t.numpy().view(shx.CELL_DTYPE)
-    nroot = 4096
-    rng = np.random.default_rng(5)
-    rxy_t = torch.empty((nroot, 2), dtype=torch.int32, pin_memory=True)  # this step's inputs, pinned as well
-    rval_t = torch.zeros(nroot, dtype=torch.float32, pin_memory=True)
-    rxy, rval = rxy_t.numpy(), rval_t.numpy()
-    rxy[:] = np.stack([rng.integers(strip.row0, strip.row1, nroot), rng.integers(0, 512 * MAPSIZE, nroot)], 1)
-    mask = shx.F_ALL if args.e2e_mask == "all" else (shx.F_HEIGHT | shx.F_DISCHARGE | shx.F_MOMENTUM)
-    rec_bytes = 32 if args.e2e_mask == "all" else 16
-    own_cells = (strip.row1 - strip.row0) * 512 * MAPSIZE
-
-    def e2e_step():
-        W.set_rootdensity(rxy, rval)     # host -> device: this step's inputs (Plant::root edits)
-        n = one_step().steps
-        W.download(out=pool, mask=mask)  # device -> host: the records the renderer / vegetation read
-        return n
-
-    e2e_steps = max(2, min(args.steps, 5))
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    mine = 0
-    for _ in range(e2e_steps):
-        mine += e2e_step()
-    barrier()
-    dt = time.perf_counter() - t0
-    tmax = torch.tensor([dt], dtype=torch.float64, device=dev)
-    tsum = torch.tensor([float(mine)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tsum)
-    del pool, pool_t
+    # ---- mature world: the same cycle after 200 more calls (rivers formed: queues, damping and cascades fire more)
+    if world == 1:
+        for _ in range(200):
+            W.erode_async(CYCLES, SEED)
+        W.sync()
+        W.timing_enable(True)
+        W.timing_read()
+        m_ms, m_acc = timed_calls(W, CYCLES, 10, 0)
+        m_tm = W.timing_read()
+        W.timing_enable(False)
+        m_steps = m_acc["steps"] / 10
+        line["mature_world"] = {"after_calls": args.warmup + args.steps + 200, "ms_per_step": m_ms, "value": m_steps / (m_ms * 1e-3), "unit": UNIT,
+                                "mean_steps_per_drop": m_acc["steps"] / max(m_acc["spawned"], 1), "phases_per_cycle": m_acc["phases"] / 10,
+                                "cascade_transfers_per_step": m_acc["cascade_transfers"] / max(m_acc["steps"], 1),
+                                "roofline_frac": m_steps * BYTES_PER_STEP / (m_tm.descend_ms / 10 * 1e-3) / 1e9 / hbm}
 
     # ---- the same loop when the per-frame consumers run on the device: no pool download; the vertex records go
     # into a device buffer (the renderer's VBO through interop) and the host reads back only the cells its
     # vegetation pass looks at (shx_gather_cells).  Reported beside e2e, not instead of it.
-    vbuf = torch.empty(own * 12, dtype=torch.float32, device=dev)
-    nq = 8192
-    qxy = np.stack([rng.integers(strip.row0 + 2, strip.row1 - 2, nq), rng.integers(0, 512 * MAPSIZE, nq)], 1).astype(np.int32)
+    if world == 1:
+        rng = np.random.default_rng(5)
+        nroot = 4096
+        rxy = np.stack([rng.integers(2, 512 * MAPSIZE - 2, nroot), rng.integers(2, 512 * MAPSIZE - 2, nroot)], 1).astype(np.int32)
+        rval = np.zeros(nroot, np.float32)
+        vbuf = torch.empty(own * 12, dtype=torch.float32, device=dev)
+        nq = 8192
+        qxy = np.stack([rng.integers(2, 512 * MAPSIZE - 2, nq), rng.integers(0, 512 * MAPSIZE, nq)], 1).astype(np.int32)
 
-    def interactive_step():
-        W.set_rootdensity(rxy, rval)
-        n = one_step().steps
-        W.vertex_fill(vbuf.data_ptr())
-        W.gather_cells(qxy)  # blocks: cells + normals on the host
-        return n
+        def interactive_step():
+            W.set_rootdensity(rxy, rval)
+            n = one_step().steps
+            W.vertex_fill(vbuf.data_ptr())
+            W.gather_cells(qxy)  # blocks: cells + normals on the host
+            return n
 
-    interactive_step()
-    barrier()
-    t0_i = time.perf_counter()
-    mine_i = 0
-    for _ in range(e2e_steps):
-        mine_i += interactive_step()
-    barrier()
-    dt_i = time.perf_counter() - t0_i
-    tmax_i = torch.tensor([dt_i], dtype=torch.float64, device=dev)
-    tsum_i = torch.tensor([float(mine_i)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax_i, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tsum_i)
-    del vbuf
-    if rank == 0:
+        interactive_step()
+        t0_i = time.perf_counter()
+        mine_i = sum(interactive_step() for _ in range(5))
+        dt_i = time.perf_counter() - t0_i
+        del vbuf
         line["e2e_device_consumers"] = {
-            "value": float(tsum_i.item()) / float(tmax_i.item()), "unit": UNIT, "ms_per_step": 1e3 * float(tmax_i.item()) / e2e_steps,
+            "value": mine_i / dt_i, "unit": UNIT, "ms_per_step": 1e3 * dt_i / 5,
             "h2d_bytes_per_step": int(rxy.nbytes + rval.nbytes + qxy.nbytes), "d2h_bytes_per_step": int(nq * (32 + 12)),
             "api": "shx_set_rootdensity + shx_erode + shx_vertex_fill (device buffer) + shx_gather_cells (8192 cells and normals to the host)"}
-    if rank == 0:
-        line["e2e"] = {"value": float(tsum.item()) / float(tmax.item()), "unit": UNIT,
-                       "h2d_bytes_per_step": int(rxy.nbytes + rval.nbytes), "d2h_bytes_per_step": int(own_cells * rec_bytes),
-                       "ms_per_step": 1e3 * float(tmax.item()) / e2e_steps, "steps": e2e_steps,
-                       "api": "shx_set_rootdensity + shx_erode + shx_download (the calls of simplehydrology_b200/host/shx_world.hpp)",
-                       "download": "full 32-byte records" if args.e2e_mask == "all" else "height+discharge+momentum (16 of 32 bytes per cell)"}
 
-    # ---- CPU baseline: the reference's own loop on the host cores, bounded sample (rank 0, N == 1)
+    # ---- the reference's own map sizes and the L2 figure they are set against (N == 1)
+    if world == 1:
+        l2_gbs = W.measure_read_bandwidth(32 << 20, 64)
+        hbm_probe = W.measure_read_bandwidth(4 << 30, 1)
+        line["l2_peak"] = {"value": l2_gbs, "unit": "GB/s", "how": "64 passes of 16-byte .cg loads over a 32-MiB buffer (L2-resident), best of 5 launches",
+                           "hbm_same_probe": hbm_probe}
+    W.close()
+    if world == 1:
+        line["configs"] = {
+            "default_512_erode512": small_config(shx, torch, 1, 512, 20, 3, l2_gbs),      # BASELINE configs[1], the reference's frame
+            "default_512_erode65536": small_config(shx, torch, 1, 65536, 2, 1, l2_gbs),   # the throughput form of configs[1]
+            "2048_erode512": small_config(shx, torch, 4, 512, 20, 3, l2_gbs)}             # BASELINE configs[2]
+
+    # ---- e2e: the C++ host adaptor's own frame on a HOST pool (rank 0 drives all N GPUs from one thread through
+    # shx_multi; the other ranks wait on the rendezvous store, not in a GPU kernel, so their devices are free)
+    if world > 1:
+        store = dist.distributed_c10d._get_default_store()
+        if rank != 0:
+            store.wait(["shx_e2e_done"], datetime.timedelta(seconds=900))
+    if rank == 0:
+        try:
+            b = run_bridge(world)
+            line["e2e"] = {"value": b["value"], "unit": UNIT, "h2d_bytes_per_step": b["h2d_bytes_per_step"], "d2h_bytes_per_step": b["d2h_bytes_per_step"],
+                           "ms_per_step": b["ms_per_step"], "steps": b["steps"], "breakdown_ms_per_step": b["breakdown_ms_per_step"],
+                           "pool_register_s": b["pool_register_s"], "rootdensity_cells_per_step": b["rootdensity_cells_per_step"], "api": b["api"],
+                           "bound": "2 GiB of 32-byte records cross PCIe per step; erode and download are sequential because the host reads the step's own result"}
+        except Exception as e:
+            line["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(e)}
+        if world > 1:
+            store.set("shx_e2e_done", "1")
+
+    # ---- roofline.traffic: DRAM bytes of one descend launch, measured by an ncu child of this run (N == 1)
+    if rank == 0 and world == 1 and not args.no_traffic:
+        line["roofline"]["traffic"], line["roofline"]["traffic_source"] = measure_traffic()
+
+    # ---- CPU baseline: the reference's own loop on the host cores, one whole cycle (rank 0, N == 1)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            W.close()
-            R = reference_world(MAPSIZE, SEED)
+            with shx.World(mapsize=MAPSIZE, mode=shx.MODE_SEQUENTIAL) as W0:  # fp32 heights: the reference's init to the bit
+                W0.init_terrain(SEED)
+                heights = W0.download(mask=shx.F_HEIGHT)["height"].copy()
+            R = reference_world(MAPSIZE, SEED, heights=heights)
+            del heights
             if R is not None:
-                drops = 8192
-                nst, secs = time_reference(R, MAPSIZE, drops, 3, 0)
+                nst, secs = time_reference(R, MAPSIZE, CYCLES, 1, 0)
                 line["cpu_baseline"] = {
                     "value": nst / secs, "unit": UNIT, "cores": 1, "kind": "reference", "host_cores": os.cpu_count(),
-                    "sample": f"3 x {drops} drops (of the cycle's {MAPSIZE * MAPSIZE * CYCLES}) on the same 8192^2 world through the reference's own "
+                    "sample": f"1 whole erode(512) call ({MAPSIZE * MAPSIZE * CYCLES} drops) on the same 8192^2 world and terrain through the reference's own "
                               f"Drop::descend / World::cascade (oracle/_ref), incl. reset + EMA passes; {secs:.1f} s of CPU"}
                 del R
                 ncores = os.cpu_count() or 1
@@ -444,8 +559,9 @@ def main():
     ap.add_argument("--steps", type=int, default=40)  # 40 cycles ~ 0.5 s timed: several clock samples
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--e2e-mask", default="all", choices=["all", "hdm"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the ncu child process that measures roofline.traffic")
+    ap.add_argument("--traffic-probe", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--replica", type=float, default=0.0, help=argparse.SUPPRESS)
     ap.add_argument("--replica-seed", type=int, default=100, help=argparse.SUPPRESS)
     ap.add_argument("--multi", default="cycle", choices=["cycle", "peer", "rounds"],
@@ -453,6 +569,8 @@ def main():
     args = ap.parse_args()
     if args.replica > 0:
         return replica_worker(args.replica, args.replica_seed)
+    if args.traffic_probe:
+        return traffic_probe()
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)

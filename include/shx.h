@@ -203,6 +203,9 @@ typedef struct {
   double d2h_ms;   /* shx_download: the device-to-host copies on the copy stream (sum over tiles; overlaps pack_ms) */
   double push_ms;  /* shx_add/set_rootdensity: host-to-device copy + kernel */
 } shx_timing;
+/* shape of the last descend launch of this context: CTAs, threads per CTA, lanes per drop (1 = one thread per drop,
+ * the dense / spread shapes; 8 = eight lanes per drop).  Results never depend on it; tests assert which kernel ran. */
+int shx_launch_info(const shx_ctx* c, int* grid, int* block, int* lanes_per_drop);
 int shx_timing_enable(shx_ctx* c, int on);
 int shx_timing_read(shx_ctx* c, shx_timing* out);
 /* same with explicit spawn points (x,y pairs, world coordinates) -- parity mode */
@@ -230,6 +233,11 @@ int shx_init_terrain(shx_ctx* c, int seed);
 /* a cheaper device-side seeded synthetic terrain (value-noise fBm normalised to [0,1]); other fields zeroed */
 int shx_synth_terrain(shx_ctx* c, uint32_t seed);
 
+/* measurement aid (bench.py): read bandwidth of `passes` streaming passes over a scratch buffer of `bytes` (16-byte
+ * .cg loads, best of 5 launches).  A buffer that fits L2 (e.g. 32 MiB) gives the L2 figure the small-map roofline is
+ * set against; one far beyond L2 reproduces the HBM figure of MEASURED_PEAKS.json. */
+int shx_measure_read_bandwidth(shx_ctx* c, size_t bytes, int passes, double* gbs);
+
 /* raw device state over the stored rows, cell index (x-xlo)*size+y (tests: bit-exact comparison
  * with the lock-step oracle).  Either pointer may be NULL.
  *   hq2:   2 int32 per cell, the two Q5.26 height planes interleaved
@@ -251,6 +259,13 @@ int shx_vertex_fill(shx_ctx* c, float* dev_out);
 int shx_vertex_download(shx_ctx* c, float* host_out, size_t ncells);
 int shx_view_maps(shx_ctx* c, float* dev_out);
 int shx_view_maps_download(shx_ctx* c, float* host_out, size_t ncells);
+/* the same two maps as the RGBA8 textures the reference uploads (SimpleHydrology.cpp:341-354): dischargeMap =
+ * vec4(waterColor, erf(0.4*discharge)), momentumMap = vec4(0.5*(1+erf(mx)), 0.5*(1+erf(my)), 0.5, 1), 4 bytes per
+ * owned cell each in map order, channels (unsigned char)(255*c).  water_rgb: 3 floats, NULL = the reference's
+ * default (92,133,142)/255 (model.h:22).  The byte packing restates TinyEngine 1.7's image::make, which is not
+ * vendored by the reference: unpinned.  Device pointers (e.g. CUDA-GL mapped textures / PBOs). */
+int shx_view_textures(shx_ctx* c, const float* water_rgb, uint8_t* dev_discharge_rgba, uint8_t* dev_momentum_rgba);
+int shx_view_textures_download(shx_ctx* c, const float* water_rgb, uint8_t* host_discharge_rgba, uint8_t* host_momentum_rgba, size_t ncells);
 /* Sparse read-back for host code that looks at a few cells per frame (Vegetation::grow: discharge /
  * height / normal / rootdensity at plant positions, vegetation.h:67-85,160-180) instead of the whole
  * pool: the records of the n queried cells {x, y} and, if normals3 != NULL, World::map.normal there

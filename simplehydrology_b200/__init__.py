@@ -103,6 +103,7 @@ def lib():
     L.shx_erode.argtypes = [vp, C.c_int, u64, C.POINTER(Stats)]
     L.shx_erode_async.argtypes = [vp, C.c_int, u64]
     L.shx_read_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.shx_launch_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.shx_timing_enable.argtypes = [vp, C.c_int]
     L.shx_timing_read.argtypes = [vp, C.POINTER(Timing)]
     L.shx_erode_spawnlist.argtypes = [vp, vp, sz, C.POINTER(Stats)]
@@ -133,6 +134,9 @@ def lib():
     L.shx_multi_sync.argtypes = [vp]
     L.shx_synth_terrain.argtypes = [vp, C.c_uint32]
     L.shx_init_terrain.argtypes = [vp, C.c_int]
+    L.shx_view_textures.argtypes = [vp, vp, vp, vp]
+    L.shx_view_textures_download.argtypes = [vp, vp, vp, vp, sz]
+    L.shx_measure_read_bandwidth.argtypes = [vp, sz, C.c_int, C.POINTER(C.c_double)]
     L.shx_download_raw.argtypes = [vp, vp, vp]
     L.shx_stored_rows.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.shx_strip_pack_halo_delta.argtypes = [vp, vp, vp]
@@ -266,6 +270,17 @@ class World:
     def synth_terrain(self, seed):
         self._check(self.L.shx_synth_terrain(self._h, seed))
 
+    def launch_info(self):
+        """(CTAs, threads per CTA, lanes per drop) of the last descend launch"""
+        g, b, l = C.c_int(), C.c_int(), C.c_int()
+        self._check(self.L.shx_launch_info(self._h, C.byref(g), C.byref(b), C.byref(l)))
+        return g.value, b.value, l.value
+
+    def measure_read_bandwidth(self, nbytes, passes):
+        g = C.c_double()
+        self._check(self.L.shx_measure_read_bandwidth(self._h, nbytes, passes, C.byref(g)))
+        return g.value
+
     def init_terrain(self, seed):
         """World::map.init(..., SEED) (cellpool.h:349-409) on the device"""
         self._check(self.L.shx_init_terrain(self._h, seed))
@@ -377,6 +392,17 @@ class World:
         out = np.zeros((n, 4), np.float32)
         self._check(self.L.shx_view_maps_download(self._h, out.ctypes.data, n))
         return out
+
+    def view_textures(self, dev_discharge, dev_momentum, water_rgb=None):
+        w = np.ascontiguousarray(water_rgb, np.float32).ctypes.data if water_rgb is not None else None
+        self._check(self.L.shx_view_textures(self._h, w, dev_discharge, dev_momentum))
+
+    def view_textures_download(self, water_rgb=None):
+        n = self.owned_cells()
+        a, b = np.zeros((n, 4), np.uint8), np.zeros((n, 4), np.uint8)
+        w = np.ascontiguousarray(water_rgb, np.float32) if water_rgb is not None else None
+        self._check(self.L.shx_view_textures_download(self._h, w.ctypes.data if w is not None else None, a.ctypes.data, b.ctypes.data, n))
+        return a, b
 
     def gather_cells(self, xy, normals=True):
         """records (CELL_DTYPE) and World::map.normal of the cells xy[n, 2] (int32)"""
@@ -490,6 +516,17 @@ class MultiWorld:
             out = np.zeros(self.ncells, CELL_DTYPE)
         self._check(self.L.shx_multi_download(self._h, out.ctypes.data, out.size, mask))
         return out
+
+    def launch_info(self):
+        """(CTAs, threads per CTA, lanes per drop) of the last descend launch"""
+        g, b, l = C.c_int(), C.c_int(), C.c_int()
+        self._check(self.L.shx_launch_info(self._h, C.byref(g), C.byref(b), C.byref(l)))
+        return g.value, b.value, l.value
+
+    def measure_read_bandwidth(self, nbytes, passes):
+        g = C.c_double()
+        self._check(self.L.shx_measure_read_bandwidth(self._h, nbytes, passes, C.byref(g)))
+        return g.value
 
     def init_terrain(self, seed):
         self._check(self.L.shx_multi_init_terrain(self._h, seed))

@@ -50,21 +50,32 @@ def build(force=False, verbose=False):
 
 
 HOST_EXAMPLE = os.path.join(HERE, "host", "example_erode")
+HOST_BENCH = os.path.join(HERE, "host", "bench_bridge")
 
 
-def build_host_example(force=False):
-    """the C++ host adaptor's example driver (plain g++, links libshx.so through the C ABI only)"""
-    src = os.path.join(HERE, "host", "example_erode.cpp")
+def _build_host(src_name, out):
+    src = os.path.join(HERE, "host", src_name)
     deps = [src, os.path.join(HERE, "host", "shx_world.hpp"), os.path.join(ROOT, "include", "shx.h"), LIB]
-    if not force and os.path.exists(HOST_EXAMPLE) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_EXAMPLE) for d in deps):
-        return HOST_EXAMPLE
+    if os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else os.environ.get("CXX", "g++")
-    cmd = [cxx, "-std=c++17", "-O2", "-Wall", src, "-o", HOST_EXAMPLE, "-L" + HERE, "-lshx", "-Wl,-rpath," + HERE]
+    cmd = [cxx, "-std=c++17", "-O2", "-Wall", src, "-o", out, "-L" + HERE, "-lshx", "-Wl,-rpath,$ORIGIN/.."]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("g++ failed building the host example")
-    return HOST_EXAMPLE
+        raise RuntimeError(f"g++ failed building {src_name}")
+    return out
+
+
+def build_host_example(force=False):
+    """the C++ host adaptor's drivers (plain g++, linked with libshx.so through the C ABI only): the example frame
+    loop and the end-to-end benchmark bench.py runs"""
+    if force:
+        for f in (HOST_EXAMPLE, HOST_BENCH):
+            if os.path.exists(f):
+                os.remove(f)
+    _build_host("bench_bridge.cpp", HOST_BENCH)
+    return _build_host("example_erode.cpp", HOST_EXAMPLE)
 
 
 if __name__ == "__main__":

@@ -98,6 +98,7 @@ struct shx_ctx {
   char* h_push = nullptr;  // pinned
   size_t push_cap = 0;
   cudaEvent_t push_done = nullptr;  // the bounce buffer may be overwritten once this has fired
+  int last_grid = 0, last_block = 0, last_lanes = 0;  // shape of the last descend launch (shx_launch_info)
   cudaAccessPolicyWindow l2_window{};  // persisting-L2 window over the height / claim words (maps that fit)
   bool l2_window_on = false;
 };
@@ -648,6 +649,33 @@ int shx_view_maps_download(shx_ctx* c, float* host_out, size_t ncells) {
   return SHX_OK;
 }
 
+int shx_view_textures(shx_ctx* c, const float* water_rgb, uint8_t* dev_discharge_rgba, uint8_t* dev_momentum_rgba) {
+  if (!c || !dev_discharge_rgba || !dev_momentum_rgba) return fail(SHX_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->cfg.device));
+  // model.h:22: waterColor = vec3(92, 133, 142) / 255.0f
+  const float3 water = water_rgb ? make_float3(water_rgb[0], water_rgb[1], water_rgb[2])
+                                 : make_float3(92.0f / 255.0f, 133.0f / 255.0f, 142.0f / 255.0f);
+  const int grid = (int)std::min<size_t>((c->owned_cells + 255) / 256, (size_t)c->sm_count * 16);
+  view_textures_kernel<<<grid, 256, 0, c->stream>>>(view_args(c), water, reinterpret_cast<unsigned*>(dev_discharge_rgba),
+                                                     reinterpret_cast<unsigned*>(dev_momentum_rgba), c->owned_cells);
+  c->launches++;
+  CU(cudaGetLastError());
+  return SHX_OK;
+}
+
+int shx_view_textures_download(shx_ctx* c, const float* water_rgb, uint8_t* host_discharge_rgba, uint8_t* host_momentum_rgba, size_t ncells) {
+  if (!c || !host_discharge_rgba || !host_momentum_rgba) return fail(SHX_ERR_ARG, "null argument");
+  if (ncells != c->owned_cells) return fail(SHX_ERR_ARG, "texture buffers must hold the owned cells");
+  int rc = view_staging(c, c->owned_cells * 8);
+  if (rc) return rc;
+  uint8_t* d = reinterpret_cast<uint8_t*>(c->d_view);
+  if ((rc = shx_view_textures(c, water_rgb, d, d + 4 * c->owned_cells))) return rc;
+  CU(cudaMemcpyAsync(host_discharge_rgba, d, 4 * c->owned_cells, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(host_momentum_rgba, d + 4 * c->owned_cells, 4 * c->owned_cells, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return SHX_OK;
+}
+
 int shx_gather_cells(shx_ctx* c, const int* xy, size_t n, shx_cell* out, float* normals3) {
   if (!c || (n && (!xy || !out))) return fail(SHX_ERR_ARG, "null argument");
   if (!n) return SHX_OK;
@@ -748,7 +776,10 @@ static int next_claim_epoch(shx_ctx* c) {
 // L2 (2048^2: 64 MiB of 16-byte cell words), the launch carries an access-policy window over them: the per-call
 // streaming passes (EMA over 32-byte records, vertex fill, view maps) then cannot evict the words every phase of
 // every drop gathers, and the phases of a latency-bound call hit L2 instead of HBM.
-static cudaError_t launch_descend(shx_ctx* c, const void* kernel, int grid, int block, void** args, size_t smem) {
+static cudaError_t launch_descend(shx_ctx* c, const void* kernel, int grid, int block, void** args, size_t smem, int lanes_per_drop) {
+  c->last_grid = grid;
+  c->last_block = block;
+  c->last_lanes = lanes_per_drop;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(block);
@@ -801,7 +832,7 @@ static int run_device_drops(shx_ctx* c, size_t n, bool trace, bool align_age = f
     c->launches++;
     void* args[] = {&a};
     const int grid = (int)std::max<size_t>(1, (n + ls.block - 1) / ls.block);
-    CU(launch_descend(c, ls.kernel, grid, ls.block, args, ls.smem(ls.block)));
+    CU(launch_descend(c, ls.kernel, grid, ls.block, args, ls.smem(ls.block), 1));
     c->launches++;
     return SHX_OK;
   }
@@ -848,7 +879,7 @@ static int run_device_drops(shx_ctx* c, size_t n, bool trace, bool align_age = f
       take = left;
       a.ndrops = (unsigned)take;
       const int block = (int)((take * 8 + 31) / 32 * 32);
-      CU(launch_descend(c, (const void*)KERNEL_SMALL, 1, block, args, (size_t)kGroupSmemWords * 4 * block));
+      CU(launch_descend(c, (const void*)KERNEL_SMALL, 1, block, args, (size_t)kGroupSmemWords * 4 * block, 8));
     } else {
       // eight lanes per drop while the whole batch is co-resident that way, one thread per drop beyond
       const LaunchShape& g = c->shape[0];
@@ -861,7 +892,7 @@ static int run_device_drops(shx_ctx* c, size_t n, bool trace, bool align_age = f
       take = std::min(left, (size_t)cap * per_block);
       a.ndrops = (unsigned)take;
       const int grid = (int)((take + per_block - 1) / per_block);
-      CU(launch_descend(c, ls.kernel, grid, block, args, ls.smem(block)));
+      CU(launch_descend(c, ls.kernel, grid, block, args, ls.smem(block), ls.group ? 8 : 1));
     }
     c->launches++;
     done += take;
@@ -892,6 +923,14 @@ static int spawn_device(shx_ctx* c, int cycles, uint64_t seed, uint64_t epoch, s
   spawn_kernel<<<grid_for(c, n), 256, 0, c->stream>>>(a);
   c->launches++;
   CU(cudaGetLastError());
+  return SHX_OK;
+}
+
+int shx_launch_info(const shx_ctx* c, int* grid, int* block, int* lanes_per_drop) {
+  if (!c) return fail(SHX_ERR_ARG, "null context");
+  if (grid) *grid = c->last_grid;
+  if (block) *block = c->last_block;
+  if (lanes_per_drop) *lanes_per_drop = c->last_lanes;
   return SHX_OK;
 }
 
@@ -1094,6 +1133,39 @@ int shx_init_terrain(shx_ctx* c, int seed) {  // map::init, cellpool.h:349-409
   int rc = refresh_halo_ref(c);
   if (rc) return rc;
   CU(cudaStreamSynchronize(c->stream));
+  return SHX_OK;
+}
+
+int shx_measure_read_bandwidth(shx_ctx* c, size_t bytes, int passes, double* gbs) {
+  if (!c || !gbs || bytes < 4096 || passes < 1) return fail(SHX_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(c->cfg.device));
+  int4* buf = nullptr;
+  const size_t n = bytes / sizeof(int4);
+  if (cudaMalloc((void**)&buf, n * sizeof(int4)) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(SHX_ERR_NOMEM, "cudaMalloc failed for the bandwidth probe");
+  }
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  CU(cudaMemsetAsync(buf, 0, n * sizeof(int4), c->stream));
+  const int grid = c->sm_count * 8;
+  read_bandwidth_kernel<<<grid, 256, 0, c->stream>>>(buf, n, 2, c->d_flags + 3);  // warm: the buffer is in L2 if it fits
+  float best = 0.0f;
+  for (int rep = 0; rep < 5; rep++) {
+    CU(cudaEventRecord(e0, c->stream));
+    read_bandwidth_kernel<<<grid, 256, 0, c->stream>>>(buf, n, passes, c->d_flags + 3);
+    CU(cudaEventRecord(e1, c->stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.0f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep == 0 || ms < best) best = ms;
+  }
+  CU(cudaGetLastError());
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  *gbs = (double)n * sizeof(int4) * passes / (best * 1e-3) / 1e9;
   return SHX_OK;
 }
 

@@ -504,4 +504,19 @@ __global__ void copy_heights_kernel(const int4* hq, int2* out, size_t n) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Bandwidth probe (shx_measure_read_bandwidth): every thread streams 16-byte .cg loads over a buffer `passes`
+// times.  With a buffer that fits L2 this measures the L2 read bandwidth the latency-regime configurations are
+// set against (MEASURED_PEAKS.json only lists HBM); with a buffer far beyond L2 it reproduces the HBM figure.
+__global__ void read_bandwidth_kernel(const int4* __restrict__ buf, size_t n, int passes, int* sink) {
+  int acc = 0;
+  for (int p = 0; p < passes; p++)
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+      const int4 v = __ldcg(buf + i);
+      acc ^= v.x ^ v.y ^ v.z ^ v.w;
+    }
+  if (acc == 0x7fffffff) *sink = acc;  // never true for a zeroed buffer: keeps the loads alive
+}
+
 }  // namespace shx

@@ -89,6 +89,26 @@ __global__ void view_maps_kernel(const ViewArgs a, float4* __restrict__ out, con
   }
 }
 
+// The two RGBA8 textures the reference uploads every frame (SimpleHydrology.cpp:341-354):
+//   dischargeMap  vec4(waterColor, erf(0.4*discharge))                       (cellpool.h:242-244 via :439)
+//   momentumMap   vec4(0.5*(1+erf(mx)), 0.5*(1+erf(my)), 0.5, 1.0)
+// one texel per cell in map order (x*size + y), each channel (unsigned char)(255*c) -- the byte packing restates
+// TinyEngine 1.7's image::make, which is NOT part of /root/reference (parity of the packing is unpinned; the
+// float values are pinned through shx_view_maps).  16 of the record's 32 bytes read, 8 bytes written per cell.
+__device__ __forceinline__ unsigned pack_rgba8(float r, float g, float b, float a) {
+  auto q = [](float c) { return (unsigned)(unsigned char)(int)(255.0f * c); };  // C++ float -> unsigned char via truncation
+  return q(r) | (q(g) << 8) | (q(b) << 16) | (q(a) << 24);
+}
+__global__ void view_textures_kernel(const ViewArgs a, const float3 water, unsigned* __restrict__ discharge_rgba,
+                                     unsigned* __restrict__ momentum_rgba, const size_t ncells) {
+  const size_t off = (size_t)(a.m.row0 - a.m.xlo) * a.m.size;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncells; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 f = __ldg(reinterpret_cast<const float4*>(a.m.rec + off + i));  // discharge momentumx momentumy rootdensity
+    discharge_rgba[i] = pack_rgba8(water.x, water.y, water.z, shx_erff(0.4f * f.x));
+    momentum_rgba[i] = pack_rgba8(0.5f * (1.0f + shx_erff(f.y)), 0.5f * (1.0f + shx_erff(f.z)), 0.5f, 1.0f);
+  }
+}
+
 // Sparse read-back for host code that only looks at a few cells per frame (Vegetation::grow reads
 // discharge / height / normal / rootdensity at plant positions, vegetation.h:67-85,160-180): the
 // 32-byte records of the queried cells and, optionally, World::map.normal there (cellpool.h:181-204

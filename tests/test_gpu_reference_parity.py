@@ -91,7 +91,7 @@ def test_check2_mass_ledger_at_full_size(mapsize, cycles):
             assert st.spawned + st.rejected == mapsize * mapsize * cycles
             assert st.spawned == st.term_age + st.term_vol + st.term_oob
             assert st.steps <= 502 * st.spawned  # water.h:74: at most maxAge + 2 descend calls per drop
-            assert st.phases == 502              # a phase spent waiting for a shared cell is a step not taken
+            assert 502 <= st.phases <= 502 + 8   # plus at most free_waits phases for drops that queued
 
 
 def _metrics(a, b, init):
@@ -186,7 +186,7 @@ def test_long_run_stays_inside_the_height_range():
                 h = W.download_height_q()[..., 0].astype(np.float64) * H_LSB
                 assert -0.01 < h.min() and h.max() < 1.01, (c, h.min(), h.max())
                 means.append(h.mean())
-        assert st.phases == 502                     # queues cost steps, not phases
+        assert 502 <= st.phases <= 502 + 8          # free waits prolong a call by at most free_waits phases
         assert abs(means[-1] - h0.mean()) < 2e-3    # no runaway of the bulk either
         m = W.view_maps_download()
         assert m[:, 0].max() > 0.99                 # rivers have formed: discharge alpha saturates somewhere

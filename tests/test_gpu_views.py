@@ -128,3 +128,22 @@ def test_device_terrain_init_in_sequential_mode_is_bit_exact(golden):
         W.init_terrain(1)
         cells = W.download()
     assert np.array_equal(cells["height"].view(np.uint32), golden["init_height"].view(np.uint32))
+
+
+def test_view_textures_are_the_packed_view_maps():
+    """shx_view_textures: the dischargeMap / momentumMap RGBA8 textures (SimpleHydrology.cpp:341-354).  Every channel is
+    (unsigned char)(255*c) of the pinned float values of shx_view_maps; water colour as model.h:22."""
+    with shx.World(mapsize=2) as W:
+        W.synth_terrain(4)
+        for _ in range(3):
+            W.erode(512, 3)
+        maps = W.view_maps_download()
+        dis, mom = W.view_textures_download()
+        dis2, _ = W.view_textures_download(water_rgb=[0.25, 0.5, 1.0])
+    q = lambda c: (np.float32(255.0) * c.astype(np.float32)).astype(np.int32).astype(np.uint8)
+    water = np.array([92, 133, 142], np.float32) / np.float32(255.0)
+    assert np.array_equal(dis[:, 3], q(maps[:, 0])) and (dis[:, :3] == q(water)).all()
+    assert np.array_equal(mom[:, 0], q(maps[:, 1])) and np.array_equal(mom[:, 1], q(maps[:, 2]))
+    assert (mom[:, 2] == 127).all() and (mom[:, 3] == 255).all()
+    assert (dis2[:, :3] == np.array([63, 127, 255], np.uint8)).all() and np.array_equal(dis2[:, 3], dis[:, 3])
+    assert dis[:, 3].max() > 100  # rivers did form

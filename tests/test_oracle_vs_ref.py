@@ -110,3 +110,29 @@ def test_terrain_init_restatement_matches_map_init(mapsize, seed):
         pytest.skip("oracle/_ref for this map size not built")
     out = orc.run_ref_script(INIT_SCRIPT % (mapsize, seed, mapsize, mapsize, seed))
     assert out.strip().startswith("OK"), out
+
+
+VIEW_SCRIPT = r"""
+import ctypes as C, numpy as np, orc
+R = orc.Ref(1, seed=1)
+rng = np.random.default_rng(3)
+for c in range(6):
+    R.erode_spawnlist(rng.integers(0, 512, size=(512, 2)).astype(np.float32))
+R.L.ref_discharge.restype = C.c_float
+p = orc.default_params(1)
+maps = orc.view_maps(p, R.cells, erf_poly=0).reshape(512, 512, 4)
+ok = True
+worst = 0.0
+for (x, y) in rng.integers(0, 512, size=(4000, 2)):
+    ok &= np.float32(R.L.ref_discharge(int(x), int(y))) == maps[x, y, 0]
+maps_p = orc.view_maps(p, R.cells, erf_poly=1).reshape(512, 512, 4)
+worst = float(np.abs(maps_p - maps).max())
+print("OK" if ok and maps[..., 0].max() > 0.5 else "MISMATCH", worst)
+"""
+
+
+def test_view_maps_restatement_matches_map_discharge():
+    """orc_view_maps' discharge channel against the reference's own World::map.discharge (cellpool.h:242-244,439-443)
+    on an eroded world: bit-identical with libm's erf; the kernels' polynomial erf differs by at most 2e-7"""
+    out = orc.run_ref_script(VIEW_SCRIPT).strip().split()
+    assert out[0] == "OK" and float(out[1]) < 2e-7, out
