@@ -495,7 +495,10 @@ def run_cuda(args):
     if world == 1:
         line["configs"] = {
             "default_512_erode512": small_config(shx, torch, 1, 512, 20, 3, l2_gbs),      # BASELINE configs[1], the reference's frame
-            "default_512_erode65536": small_config(shx, torch, 1, 65536, 2, 1, l2_gbs),   # the throughput form of configs[1]
+            # a call with more cycles runs as consecutive batches of 512 drops per node between one reset and one EMA
+            # (SURVEY.md 8d asks for erode(65536): that many visits of one river cell overflow the Q13.18 tracks, which
+            # the library reports as SHX_ERR_RANGE instead of wrapping; 4096 is the same regime inside the range)
+            "default_512_erode4096": small_config(shx, torch, 1, 4096, 3, 1, l2_gbs),
             "2048_erode512": small_config(shx, torch, 4, 512, 20, 3, l2_gbs)}             # BASELINE configs[2]
 
     # ---- e2e: the C++ host adaptor's own frame on a HOST pool (rank 0 drives all N GPUs from one thread through
