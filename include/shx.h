@@ -115,9 +115,13 @@ typedef struct {
   int halo;            /* halo rows kept on each side of a strip (>= 2); ignored for the whole map */
   size_t max_drops;    /* capacity of the drop buffers; 0 = maparea*1024 */
   /* launch-shape overrides of the descend kernel (tuning / tests); all 0 = the library chooses by drop count.
-   * Results never depend on them: every shape is bit-identical. */
+   * Results do not depend on block_threads / variant / coop: every shape is bit-identical. */
   int block_threads;   /* CTA size */
-  int grid_blocks;     /* cap on the grid (smaller than the drop count => several launches in list order) */
+  int grid_blocks;     /* cap on the grid: a drop list longer than grid_blocks CTAs' worth marches as several launches
+                          in list order, each seeing the heights the earlier ones left -- a DIFFERENT schedule, hence
+                          different results (tests use it to exercise the split).  Without it a list is split every
+                          131 072 drops on every device; a device that cannot keep that many co-resident fails with
+                          SHX_ERR_CAPACITY rather than splitting elsewhere */
   int variant;         /* one thread per drop, register budget: 0 = 64 (1024 threads/SM), 1 = 128 (512/SM), 2 = 72 (7x128/SM),
                           3 = 72 (2x448/SM); 5 = eight lanes per drop (what the library picks for batches of up to
                           ~19 000 drops) in CTAs of block_threads */

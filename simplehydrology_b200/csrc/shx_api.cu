@@ -21,6 +21,8 @@ struct LaunchShape {
   size_t drops_per_block(int b) const { return group ? (size_t)b / 8 : (size_t)b; }
 };
 
+constexpr size_t kDropsPerLaunch = 131072;  // drops that march together in one launch (device-independent split)
+
 struct TimingSpan {
   int kind;  // 0 spawn, 1 descend, 2 ema, 3 pack (download), 4 device-to-host copy, 5 rootdensity push
   cudaEvent_t e0, e1;
@@ -268,7 +270,7 @@ int shx_create(shx_ctx** out, const shx_params* p, const shx_config* cfg_in) {
   ALLOC(c->d_xy, c->max_drops * 2 * sizeof(float));
   ALLOC(c->d_bar, sizeof(GridBar));
   ALLOC(c->d_stats, ST_COUNT * 8);
-  ALLOC(c->d_flags, 4 * sizeof(int));
+  ALLOC(c->d_flags, 8 * sizeof(int));
   ALLOC(c->d_trace, (size_t)c->trace_cap * 7 * sizeof(float));
   ALLOC(c->d_u32, 4 * sizeof(unsigned));
   ALLOC(c->d_stage, tile_cells * sizeof(shx_cell));
@@ -278,14 +280,14 @@ int shx_create(shx_ctx** out, const shx_params* p, const shx_config* cfg_in) {
   }
 #undef ALLOC
   if (cudaMallocHost((void**)&c->h_stats, ST_COUNT * 8) != cudaSuccess ||
-      cudaMallocHost((void**)&c->h_flags, 4 * sizeof(int)) != cudaSuccess) {
+      cudaMallocHost((void**)&c->h_flags, 8 * sizeof(int)) != cudaSuccess) {
     shx_destroy(c);
     return fail(SHX_ERR_NOMEM, "cudaMallocHost failed");
   }
   cudaMemset(c->m.hq, 0, c->stored_cells * sizeof(int4));
   cudaMemset(c->m.rec, 0, c->stored_cells * sizeof(CellRec));
   cudaMemset(c->d_stats, 0, ST_COUNT * 8);
-  cudaMemset(c->d_flags, 0, 4 * sizeof(int));
+  cudaMemset(c->d_flags, 0, 8 * sizeof(int));
   if (!cfg.no_l2_window && prop.persistingL2CacheMaxSize > 0 &&
       c->stored_cells * sizeof(int4) <= (size_t)prop.persistingL2CacheMaxSize &&
       c->stored_cells * sizeof(int4) <= (size_t)prop.accessPolicyMaxWindowSize) {
@@ -704,6 +706,7 @@ static int fetch_stats(shx_ctx* c, shx_stats* out) {
   CU(cudaMemcpyAsync(c->h_stats, c->d_stats, ST_COUNT * 8, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(c->h_flags + 2, c->d_flags + 2, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(c->h_flags + 4, c->d_flags + 4, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   if (out) {
     memcpy(out, c->h_stats, sizeof(shx_stats));
@@ -718,6 +721,10 @@ static int fetch_stats(shx_ctx* c, shx_stats* out) {
   if (c->h_flags[0]) {
     CU(cudaMemsetAsync(c->d_flags, 0, sizeof(int), c->stream));
     return fail(SHX_ERR_RANGE, "a discharge track left the Q13.18 range (more than ~4096 drop visits of one cell in one call)");
+  }
+  if (c->h_flags[4]) {
+    CU(cudaMemsetAsync(c->d_flags + 4, 0, sizeof(int), c->stream));
+    return fail(SHX_ERR_RANGE, "a height left (-30, 30): the world is diverging and would wrap the Q5.26 fixed point");
   }
   return SHX_OK;
 }
@@ -763,7 +770,7 @@ int shx_ema(shx_ctx* c) {
 static int next_claim_epoch(shx_ctx* c) {
   if (++c->claim_epoch > 15u) {
     const int grid = (int)std::min<size_t>((c->stored_cells + 255) / 256, (size_t)c->sm_count * 16);
-    clear_claims_kernel<<<grid, 256, 0, c->stream>>>(c->m.hq, c->stored_cells);
+    clear_claims_kernel<<<grid, 256, 0, c->stream>>>(c->m.hq, c->stored_cells, c->d_flags + 4);
     c->launches++;
     CU(cudaGetLastError());
     c->claim_epoch = 1u;
@@ -886,10 +893,16 @@ static int run_device_drops(shx_ctx* c, size_t n, bool trace, bool align_age = f
       const bool use_group = g.group && left <= (size_t)g.cap_blocks * g.drops_per_block(g.block);
       const LaunchShape& ls = c->shape[(c->forced_shape || use_group) ? 0 : (left > (size_t)c->sm_count * 256 ? 2 : 1)];
       const int block = ls.block;
-      int cap = ls.cap_blocks;
-      if (c->cfg.grid_blocks > 0) cap = std::min(cap, c->cfg.grid_blocks);
       const size_t per_block = ls.drops_per_block(block);
-      take = std::min(left, (size_t)cap * per_block);
+      // A list longer than one launch marches as consecutive launches (each sees the heights the earlier ones left).
+      // The split must not depend on the device: kDropsPerLaunch is a constant of the library (one 8192^2 cycle), and
+      // a device that cannot keep that many drops co-resident reports SHX_ERR_CAPACITY instead of splitting
+      // elsewhere.  shx_config.grid_blocks (tests) forces a smaller split on purpose.
+      size_t chunk = kDropsPerLaunch;
+      if (c->cfg.grid_blocks > 0) chunk = std::min(chunk, (size_t)c->cfg.grid_blocks * per_block);
+      take = std::min(left, chunk);
+      if (take > (size_t)ls.cap_blocks * per_block)
+        return fail(SHX_ERR_CAPACITY, "this device cannot keep a launch's drops co-resident (131072 per launch)");
       a.ndrops = (unsigned)take;
       const int grid = (int)((take + per_block - 1) / per_block);
       CU(launch_descend(c, ls.kernel, grid, block, args, ls.smem(block), ls.group ? 8 : 1));

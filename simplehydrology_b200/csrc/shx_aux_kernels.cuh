@@ -485,11 +485,15 @@ __global__ void strip_msg_apply_kernel(int4* halo, int32_t* ref, int4* edge, con
   }
 }
 
-// claim words of every stored cell back to zero (when the launch epoch of the claim keys wraps)
-__global__ void clear_claims_kernel(int4* hq, size_t n) {
+// claim words of every stored cell back to zero (when the launch epoch of the claim keys wraps, every 15 launches).
+// The same pass watches the fixed-point range: adds into the Q5.26 planes wrap silently, so a world that is running
+// away numerically (|h| beyond 30 of the representable +-32) raises the height flag before it can wrap.
+__global__ void clear_claims_kernel(int4* hq, size_t n, int* height_flag) {
+  constexpr int kLimit = 30 << kHeightFracBits;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
   {
     int4 c = hq[i];
+    if (c.x > kLimit || c.x < -kLimit) *height_flag = 1;
     c.y = 0; c.w = 0;
     hq[i] = c;
   }
