@@ -9,6 +9,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import simplehydrology_b200 as shx  # noqa: E402
 
+if os.environ.get("SHX_LIB"):  # tools/variants.py: a build with extra -D switches
+    shx.LIB_PATH = os.environ["SHX_LIB"]
+
 
 def run(ms, block, variant, grid, coop=0, cycles=512, warm=4, n=6):
     W = shx.World(mapsize=ms, block_threads=block, variant=variant, grid_blocks=grid, coop=coop)
