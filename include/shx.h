@@ -277,6 +277,43 @@ int shx_view_textures_download(shx_ctx* c, const float* water_rgb, uint8_t* host
  * the map (map.get() == NULL in the reference) or outside a strip's stored rows returns zeros. */
 int shx_gather_cells(shx_ctx* c, const int* xy, size_t n, shx_cell* out, float* normals3);
 
+/* ---- N3: Vegetation::grow() on the device (reference source/vegetation.h:122-188).
+ * The plant list and the rootdensity stamps live on the GPU, so a coupled frame (World::erode, Vegetation::grow,
+ * updatenode, tree placement: SimpleHydrology.cpp:319-335) needs no pool download and no rootdensity push.  The
+ * predicates and arithmetic are the reference's (Plant::grow :67-69, ::die :71-78, ::spawn :80-89, ::root :91-120);
+ * the schedule is the parallel one described in simplehydrology_b200/csrc/shx_veg_kernels.cuh: every plant decides
+ * from the maps as they are when the call starts, rand() is a counter hash keyed (seed, frame, cell), rootdensity is
+ * an exact count of fifths (1.0 / 0.6 / 0.4 = 5 / 3 / 2) whose fp32 value is count/5.  Deterministic and run-to-run
+ * identical; against the reference's sequential walk it is statistical (tests/test_gpu_vegetation.py).
+ * Whole-map contexts only (not strips). */
+typedef struct {
+  float maxSize, growRate, maxSteep, maxDischarge, maxTreeHeight; /* Plant:: statics, vegetation.h:40-44 */
+} shx_plant_params;
+typedef struct {
+  uint64_t plants;   /* in the list after the call */
+  uint64_t born;     /* seeded + children of this call (root(+1) stamped) */
+  uint64_t died;     /* removed by this call (root(-1) stamped) */
+  uint64_t refused;  /* children that did not fit max_plants (not created, not stamped) */
+} shx_veg_stats;
+void shx_default_plant_params(shx_plant_params* pp);
+/* allocate the plant store (max_plants == 0: one plant per four cells); pp == NULL: the reference's defaults */
+int shx_veg_create(shx_ctx* c, size_t max_plants, const shx_plant_params* pp);
+int shx_veg_set_params(shx_ctx* c, const shx_plant_params* pp);
+/* == Vegetation::grow(), once; `frame` numbers the calls (it keys the hash together with `seed`).  Returns
+ * SHX_ERR_CAPACITY (after doing the frame with the surplus children refused) if the list is full. */
+int shx_veg_grow(shx_ctx* c, uint64_t seed, uint64_t frame, shx_veg_stats* out);
+int shx_veg_count(shx_ctx* c, size_t* n);
+/* the list as {pos.x, pos.y, size} per plant (Vegetation::plants), host buffer of 3*cap floats */
+int shx_veg_download(shx_ctx* c, float* xys3, size_t cap, size_t* n);
+/* replace the list by the host's plants; stamp_roots != 0 also applies their root(+1) stamps (a list whose roots
+ * are already in the uploaded pool's rootdensity passes 0) */
+int shx_veg_upload(shx_ctx* c, const float* xys3, size_t n, int stamp_roots);
+/* the tree particle system's model matrices (SimpleHydrology.cpp:329-335): translate(pos.x, size +
+ * mapscale*height(pos), pos.y) * scale(size), 16 floats per plant, column-major (glm::mat4), into DEVICE memory
+ * (e.g. the instance buffer mapped through CUDA-GL interop) / into a host buffer */
+int shx_veg_tree_models(shx_ctx* c, float* dev_out16, size_t cap, size_t* n);
+int shx_veg_tree_models_download(shx_ctx* c, float* host_out16, size_t cap, size_t* n);
+
 /* ---- row-strip exchange (multi-GPU): buffers are DEVICE pointers owned by the caller
  * (e.g. torch tensors); the transport between ranks is the caller's (NCCL send/recv or P2P). */
 /* height deltas this strip accumulated in its halo rows since the last refresh: `halo`*size int32 per side */

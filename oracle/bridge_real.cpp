@@ -5,7 +5,10 @@
 //     real types, and that quad::cell is the 32-byte record include/shx.h declares (cellpool.h:207-220);
 //   * the coupled run of BASELINE configs[4]: SimpleHydrology.cpp:314-324's frame loop with bridge.erode in the
 //     place of world.erode (line 319), followed by the UNCHANGED Vegetation::grow() (line 320) on the host pool.
-// usage: bridge_real <seed> <frames> <out.bin> [ngpu]     (out: the cell pool, then uint64 n, then n x {x, y, size})
+//   * with device_veg = 1: the same loop with Vegetation::grow on the device as well (bridge.erode_resident +
+//     bridge.grow<Plant>, N3), instantiated against the reference's real Plant; the host pool and Vegetation::plants
+//     are filled once at the end.
+// usage: bridge_real <seed> <frames> <out.bin> [ngpu] [device_veg]   (out: the cell pool, then uint64 n, then n x {x, y, size})
 // Runs on the GPU box (the binary travels with the snapshot; /root/reference is only needed to build it).
 #include <glm/glm.hpp>
 #include "vertexpool_stub.h"
@@ -42,6 +45,7 @@ int main(int argc, char** argv) {
   }
   const int seed = atoi(argv[1]), frames = atoi(argv[2]);
   const int ngpu = argc > 4 ? atoi(argv[4]) : 1;
+  const bool device_veg = argc > 5 && atoi(argv[5]) != 0;
   World::SEED = seed;  // SimpleHydrology.cpp:27-38
   srand(seed);
   cellpool.reserve(quad::area);
@@ -61,12 +65,19 @@ int main(int argc, char** argv) {
   size_t pushed = 0;
   try {
     shx::Bridge bridge(cellpool.root.start, quad::mapsize, quad::tilesize, ngpu, nullptr, true, false);
+    if (device_veg) bridge.enable_device_vegetation<Plant>();
     for (int f = 0; f < frames; f++) {
+      if (device_veg) {
+        steps += bridge.erode_resident<Drop, World>(quad::tilesize).steps;                                // :319
+        bridge.grow<Plant>((uint64_t)World::SEED, (uint64_t)f, f == frames - 1 ? &Vegetation::plants : nullptr);  // :320 on the device
+        continue;
+      }
       const shx_stats st = bridge.erode<Drop, World>(quad::tilesize, &Vegetation::plants);  // SimpleHydrology.cpp:319
       Vegetation::grow();                                                                  // :320, unchanged
       steps += st.steps;
       pushed += bridge.last_push();
     }
+    if (device_veg) bridge.sync_pool();
     bridge.update_vertices(vertices.data());  // :322-324 on the device
   } catch (const std::exception& e) {
     fprintf(stderr, "error: %s\n", e.what());

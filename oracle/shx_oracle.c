@@ -789,7 +789,8 @@ void orc_ls_run(orc_ls_world* w, orc_drop* drops, size_t n, orc_stats* st, float
 }
 
 void orc_ls_reset_tracks(orc_ls_world* w) { /* world.h:56-61 */
-  memset(w->track, 0, sizeof(orc_track) * (size_t)w->size * w->size);
+  const size_t n = (size_t)w->size * w->size;
+  for (size_t i = 0; i < n; i++) w->track[i].discharge = w->track[i].momentumx = w->track[i].momentumy = 0; /* pad = root count */
 }
 
 /* world.h:81-86; returns 1 if a discharge accumulator left the Q13.18 range (the product then
@@ -842,6 +843,165 @@ void orc_ls_erode(orc_ls_world* w, int cycles, uint64_t seed, uint64_t epoch, or
 }
 
 /* ================================================================== synthetic terrain */
+
+/* ------------------------------------------------------------------------------------------------
+ * Vegetation::grow (vegetation.h:122-188) under the parallel schedule of the device path
+ * (simplehydrology_b200/csrc/shx_veg_kernels.cuh): every plant decides from the maps as they are at the start of the
+ * frame, rand() is a counter hash keyed (seed, frame, cell, size bits), rootdensity is a count of fifths
+ * (orc_track.pad) whose fp32 value is count / 5.  List order: survivors, the seeded plant, children by parent. */
+void orc_default_plant_params(orc_plant_params* pp) { /* vegetation.h:40-44 */
+  pp->maxSize = 1.5f;
+  pp->growRate = 0.05f;
+  pp->maxSteep = 0.8f;
+  pp->maxDischarge = 0.3f;
+  pp->maxTreeHeight = 0.8f;
+}
+
+static float veg_height(const orc_ls_world* w, int x, int y) { return hf(w->h[0][(size_t)x * w->size + y]); }
+
+static float veg_normal_y(const orc_ls_world* w, int x, int y) { /* cellpool.h:181-204, map-level oob :413-419 */
+  const int size = w->size;
+  const float scale = (float)w->p.mapscale;
+  const float hc = veg_height(w, x, y);
+  const int xm = x > 0, xp = x < size - 1, ym = y > 0, yp = y < size - 1;
+  const float hxp = xp ? veg_height(w, x + 1, y) : 0.0f, hxm = xm ? veg_height(w, x - 1, y) : 0.0f;
+  const float hyp = yp ? veg_height(w, x, y + 1) : 0.0f, hym = ym ? veg_height(w, x, y - 1) : 0.0f;
+  const float Bp = scale * (hxp - hc), Bm = scale * (hxm - hc);
+  const float Ap = scale * (hyp - hc), Am = scale * (hym - hc);
+  float nx = 0.0f, ny = 0.0f, nz = 0.0f;
+  if (xp && yp) { nx += -Bp; ny += 1.0f; nz += -Ap; }
+  if (xm && ym) { nx += Bm; ny += 1.0f; nz += Am; }
+  if (xp && ym) { nx += -Bp; ny += 1.0f; nz += Am; }
+  if (xm && yp) { nx += Bm; ny += 1.0f; nz += -Ap; }
+  const float l2 = nx * nx + ny * ny + nz * nz;
+  if (l2 > 0.0f) ny *= 1.0f / sqrtf(l2);
+  return ny;
+}
+
+static float veg_discharge(const orc_ls_world* w, int x, int y) { /* cellpool.h:242-244 with the kernels' erf */
+  return orc_erff_poly(0.4f * w->field[4 * ((size_t)x * w->size + y)]);
+}
+
+static void veg_stamp(orc_ls_world* w, int x, int y, int sign) { /* Plant::root, vegetation.h:91-120, in fifths */
+  for (int dx = -1; dx <= 1; dx++)
+    for (int dy = -1; dy <= 1; dy++) {
+      const int cx = x + dx, cy = y + dy;
+      if (ls_oob(w, cx, cy)) continue;
+      w->track[(size_t)cx * w->size + cy].pad += sign * ((dx == 0 && dy == 0) ? 5 : ((dx == 0 || dy == 0) ? 3 : 2));
+    }
+}
+
+static void veg_refresh(orc_ls_world* w, int x, int y) {
+  for (int dx = -1; dx <= 1; dx++)
+    for (int dy = -1; dy <= 1; dy++) {
+      const int cx = x + dx, cy = y + dy;
+      if (ls_oob(w, cx, cy)) continue;
+      const size_t i = (size_t)cx * w->size + cy;
+      w->field[4 * i + 3] = (float)w->track[i].pad / 5.0f;
+    }
+}
+
+void orc_veg_sync_counts(orc_ls_world* w) { /* count = round(5 * rootdensity) */
+  const size_t n = (size_t)w->size * w->size;
+  for (size_t i = 0; i < n; i++) w->track[i].pad = (int32_t)lrintf(w->field[4 * i + 3] * 5.0f);
+}
+
+void orc_veg_stamp_list(orc_ls_world* w, const orc_plant* plants, size_t n) { /* root(+1) of every listed plant */
+  for (size_t i = 0; i < n; i++) veg_stamp(w, plants[i].x, plants[i].y, +1);
+  for (size_t i = 0; i < n; i++) veg_refresh(w, plants[i].x, plants[i].y);
+}
+
+size_t orc_veg_grow(orc_ls_world* w, const orc_plant_params* pp, uint64_t seed, uint64_t frame, orc_plant* plants, size_t n,
+                    size_t cap, orc_veg_stats* st) {
+  const uint64_t key = mix64(mix64(seed) + frame);
+  const int size = w->size;
+  unsigned* fl = (unsigned*)calloc(n + 1, sizeof(unsigned));
+  int* child = (int*)calloc(2 * (n + 1), sizeof(int));
+  float* grown = (float*)calloc(n + 1, sizeof(float));
+  size_t surv = 0, kids = 0;
+  for (size_t i = 0; i < n; i++) { /* decisions from the frozen maps */
+    const int x = plants[i].x, y = plants[i].y;
+    const float s0 = plants[i].size;
+    uint32_t sbits;
+    memcpy(&sbits, &s0, 4);
+    grown[i] = s0 + pp->growRate * (pp->maxSize - s0); /* vegetation.h:67-69 */
+    const uint64_t r = mix64(key + (((uint64_t)(uint32_t)x << 32) | (uint32_t)y) + (uint64_t)sbits * 0x9E3779B97F4A7C15ull);
+    const int die = veg_discharge(w, x, y) >= pp->maxDischarge || veg_height(w, x, y) >= pp->maxTreeHeight ||
+                    (uint32_t)r % 1000u == 0u; /* :71-78 */
+    if (die) {
+      fl[i] = 4u;
+      continue;
+    }
+    fl[i] = 1u;
+    surv++;
+    if ((uint32_t)(r >> 32) % 20u != 0u) continue; /* :157 */
+    const uint64_t q = mix64(r);
+    const int nx = x + (int)((uint32_t)q % 9u) - 4, ny = y + (int)((uint32_t)(q >> 32) % 9u) - 4; /* :161 */
+    if (ls_oob(w, nx, ny)) continue;                              /* :164 */
+    if (veg_discharge(w, nx, ny) >= pp->maxDischarge) continue;   /* :167 */
+    const uint32_t r5 = (uint32_t)mix64(q) % 1000u;
+    if ((double)(float)r5 / 1000.0 <= (double)w->field[4 * ((size_t)nx * size + ny) + 3]) continue; /* :170 */
+    if (!(veg_normal_y(w, nx, ny) > pp->maxSteep)) continue;      /* :175 */
+    fl[i] |= 2u;
+    child[2 * i] = nx;
+    child[2 * i + 1] = ny;
+    kids++;
+  }
+  { /* :126-137: one seeding attempt anywhere, Plant::spawn :80-89 */
+    const uint64_t r = mix64(key ^ 0x5EED5EED5EED5EEDull);
+    const int x = (int)((uint32_t)r % (uint32_t)size), y = (int)((uint32_t)(r >> 32) % (uint32_t)size);
+    if (veg_discharge(w, x, y) < pp->maxDischarge && !(veg_normal_y(w, x, y) < pp->maxSteep) && veg_height(w, x, y) < pp->maxTreeHeight) {
+      fl[n] = 2u;
+      child[2 * n] = x;
+      child[2 * n + 1] = y;
+      kids++;
+    }
+  }
+  const size_t room = cap > surv ? cap - surv : 0, kept = kids < room ? kids : room;
+  orc_plant* out = (orc_plant*)malloc(sizeof(orc_plant) * (surv + kept + 1));
+  size_t at = 0;
+  for (size_t i = 0; i < n; i++)
+    if (fl[i] & 1u) {
+      out[at].x = plants[i].x;
+      out[at].y = plants[i].y;
+      out[at].size = grown[i];
+      at++;
+    }
+  size_t rank = 0;
+  for (size_t k = 0; k <= n; k++) { /* newcomers: the seeded plant first, then the children by parent */
+    const size_t i = k == 0 ? n : k - 1;
+    if (!(fl[i] & 2u)) continue;
+    if (rank < kept) {
+      out[at].x = child[2 * i];
+      out[at].y = child[2 * i + 1];
+      out[at].size = 0.0f;
+      at++;
+      veg_stamp(w, child[2 * i], child[2 * i + 1], +1);
+    } else {
+      fl[i] &= ~2u; /* refused: no stamp */
+    }
+    rank++;
+  }
+  for (size_t i = 0; i < n; i++)
+    if (fl[i] & 4u) veg_stamp(w, plants[i].x, plants[i].y, -1);
+  for (size_t i = 0; i <= n; i++) {
+    if (i < n && (fl[i] & 4u)) veg_refresh(w, plants[i].x, plants[i].y);
+    if (fl[i] & 2u) veg_refresh(w, child[2 * i], child[2 * i + 1]);
+  }
+  memcpy(plants, out, sizeof(orc_plant) * at);
+  if (st) {
+    st->plants = at;
+    st->born = kept;
+    st->died = n - surv;
+    st->refused = kids - kept;
+  }
+  free(out);
+  free(fl);
+  free(child);
+  free(grown);
+  return at;
+}
+
 
 static uint32_t hash2(uint32_t x, uint32_t y, uint32_t s) {
   uint32_t h = x * 0x9E3779B1u ^ y * 0x85EBCA77u ^ s * 0xC2B2AE3Du;

@@ -156,6 +156,18 @@ int orc_ls_ema(orc_ls_world* w, int reset); /* world.h:81-86 (+ :56-61 when rese
 void orc_ls_erode(orc_ls_world* w, int cycles, uint64_t seed, uint64_t epoch, orc_stats* st);
 void orc_ls_erode_spawnlist(orc_ls_world* w, const float* xy, size_t n, orc_stats* st);
 
+/* ---- Vegetation::grow (vegetation.h:122-188) under the device path's parallel schedule (see shx_veg_kernels.cuh):
+ * bit-exact checker of shx_veg_grow.  The rootdensity count (fifths) lives in orc_track.pad. */
+typedef struct { float maxSize, growRate, maxSteep, maxDischarge, maxTreeHeight; } orc_plant_params; /* vegetation.h:40-44 */
+typedef struct { int x, y; float size; } orc_plant;
+typedef struct { uint64_t plants, born, died, refused; } orc_veg_stats;
+void orc_default_plant_params(orc_plant_params* pp);
+void orc_veg_sync_counts(orc_ls_world* w);
+void orc_veg_stamp_list(orc_ls_world* w, const orc_plant* plants, size_t n); /* shx_veg_upload(stamp_roots = 1) */
+/* one frame; `plants` (capacity cap) is updated in place, returns the new count */
+size_t orc_veg_grow(orc_ls_world* w, const orc_plant_params* pp, uint64_t seed, uint64_t frame, orc_plant* plants, size_t n,
+                    size_t cap, orc_veg_stats* st);
+
 /* ---- synthetic seeded terrain (value-noise fBm, normalised to [0,1]); planar x*size+y */
 void orc_synth_terrain(float* height, int size, uint32_t seed);
 /* map::init (cellpool.h:349-409): the reference's own terrain, 8 layers of 3-octave OpenSimplex2 fBm (vendored

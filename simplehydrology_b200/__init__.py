@@ -65,6 +65,15 @@ class Stats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class PlantParams(C.Structure):
+    """Plant:: statics, vegetation.h:40-44"""
+    _fields_ = [(n, C.c_float) for n in ("maxSize", "growRate", "maxSteep", "maxDischarge", "maxTreeHeight")]
+
+
+class VegStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("plants", "born", "died", "refused")]
+
+
 class Timing(C.Structure):
     _fields_ = [("spawn_ms", C.c_double), ("descend_ms", C.c_double), ("ema_ms", C.c_double),
                 ("descend_launches", C.c_uint64), ("pack_ms", C.c_double), ("d2h_ms", C.c_double), ("push_ms", C.c_double)]
@@ -151,6 +160,16 @@ def lib():
     L.shx_view_maps.argtypes = [vp, vp]
     L.shx_view_maps_download.argtypes = [vp, vp, sz]
     L.shx_gather_cells.argtypes = [vp, vp, sz, vp, vp]
+    L.shx_default_plant_params.argtypes = [C.POINTER(PlantParams)]
+    L.shx_default_plant_params.restype = None
+    L.shx_veg_create.argtypes = [vp, sz, C.POINTER(PlantParams)]
+    L.shx_veg_set_params.argtypes = [vp, C.POINTER(PlantParams)]
+    L.shx_veg_grow.argtypes = [vp, u64, u64, C.POINTER(VegStats)]
+    L.shx_veg_count.argtypes = [vp, C.POINTER(sz)]
+    L.shx_veg_download.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    L.shx_veg_upload.argtypes = [vp, vp, sz, C.c_int]
+    L.shx_veg_tree_models.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    L.shx_veg_tree_models_download.argtypes = [vp, vp, sz, C.POINTER(sz)]
     L.shx_strip_message_words.argtypes = [vp, sz]
     L.shx_strip_message_words.restype = sz
     L.shx_strip_pack_message.argtypes = [vp, vp, vp, sz]
@@ -412,6 +431,43 @@ class World:
         nrm = np.zeros((n, 3), np.float32) if normals else None
         self._check(self.L.shx_gather_cells(self._h, xy.ctypes.data, n, out.ctypes.data, nrm.ctypes.data if normals else None))
         return (out, nrm) if normals else out
+
+    # ---- N3: Vegetation::grow on the device (vegetation.h:122-188)
+    def veg_create(self, max_plants=0, plant_params=None):
+        self._check(self.L.shx_veg_create(self._h, max_plants, C.byref(plant_params) if plant_params is not None else None))
+
+    def veg_grow(self, seed, frame):
+        st = VegStats()
+        self._check(self.L.shx_veg_grow(self._h, seed, frame, C.byref(st)))
+        return st
+
+    def veg_count(self):
+        n = C.c_size_t()
+        self._check(self.L.shx_veg_count(self._h, C.byref(n)))
+        return int(n.value)
+
+    def veg_plants(self):
+        """the plant list as float32 [n, 3] = {pos.x, pos.y, size} (Vegetation::plants)"""
+        n = self.veg_count()
+        out = np.zeros((n, 3), np.float32)
+        got = C.c_size_t()
+        self._check(self.L.shx_veg_download(self._h, out.ctypes.data, n, C.byref(got)))
+        return out
+
+    def veg_upload(self, plants, stamp_roots=True):
+        plants = np.ascontiguousarray(plants, np.float32).reshape(-1, 3)
+        self._check(self.L.shx_veg_upload(self._h, plants.ctypes.data, plants.shape[0], 1 if stamp_roots else 0))
+
+    def veg_tree_models(self, dev_ptr=None):
+        """glm::mat4 per plant (SimpleHydrology.cpp:329-335); into device memory, or returned as float32 [n, 16]"""
+        n = self.veg_count()
+        got = C.c_size_t()
+        if dev_ptr is not None:
+            self._check(self.L.shx_veg_tree_models(self._h, dev_ptr, n, C.byref(got)))
+            return n
+        out = np.zeros((n, 16), np.float32)
+        self._check(self.L.shx_veg_tree_models_download(self._h, out.ctypes.data, n, C.byref(got)))
+        return out
 
     def strip_message_words(self, cap):
         return int(self.L.shx_strip_message_words(self._h, cap))

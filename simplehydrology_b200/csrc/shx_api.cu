@@ -103,6 +103,20 @@ struct shx_ctx {
   int last_grid = 0, last_block = 0, last_lanes = 0;  // shape of the last descend launch (shx_launch_info)
   cudaAccessPolicyWindow l2_window{};  // persisting-L2 window over the height / claim words (maps that fit)
   bool l2_window_on = false;
+  // N3: vegetation on the device (shx_veg_*): two plant lists (compaction goes from one to the other), per-slot scratch
+  bool veg = false;
+  PlantParams plant{};
+  size_t veg_cap = 0, veg_n = 0;
+  int veg_cur = 0;
+  int2* d_plant_pos[2] = {nullptr, nullptr};
+  float* d_plant_size[2] = {nullptr, nullptr};
+  unsigned* d_veg_flags = nullptr;
+  int2* d_veg_child = nullptr;
+  float* d_veg_grown = nullptr;
+  uint2* d_veg_blocks = nullptr;
+  unsigned* d_veg_totals = nullptr;
+  unsigned* h_veg_totals = nullptr;  // pinned
+  bool root_counts_valid = false;    // the integer root counts mirror the fp32 rootdensity of every cell
 };
 
 static StepParams step_params(const shx_params& p) {
@@ -200,6 +214,9 @@ void shx_destroy(shx_ctx* c) {
   if (c->push_done) cudaEventDestroy(c->push_done);
   if (c->h_stats) cudaFreeHost(c->h_stats);
   if (c->h_flags) cudaFreeHost(c->h_flags);
+  for (int i = 0; i < 2; i++) { cudaFree(c->d_plant_pos[i]); cudaFree(c->d_plant_size[i]); }
+  cudaFree(c->d_veg_flags); cudaFree(c->d_veg_child); cudaFree(c->d_veg_grown); cudaFree(c->d_veg_blocks); cudaFree(c->d_veg_totals);
+  if (c->h_veg_totals) cudaFreeHost(c->h_veg_totals);
   delete c;
 }
 
@@ -476,6 +493,7 @@ int shx_upload(shx_ctx* c, const shx_cell* pool, size_t ncells) {
   }
   CU(cudaGetLastError());
   c->tracks_clean = false;  // the host's track values were taken over as they are
+  c->root_counts_valid = false;
   int rc = refresh_halo_ref(c);
   if (rc) return rc;
   CU(cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -1109,6 +1127,7 @@ static int push_rootdensity(shx_ctx* c, const int* xy, const float* delta, size_
   CU(cudaEventRecord(c->push_done, c->stream));
   const int* d_xy = reinterpret_cast<const int*>(c->d_push);
   const float* d_val = reinterpret_cast<const float*>(c->d_push + b_xy);
+  c->root_counts_valid = false;
   if (absolute) set_rootdensity_kernel<<<grid_for(c, n), 256, 0, c->stream>>>(c->m, d_xy, d_val, n);
   else add_rootdensity_kernel<<<1, 1, 0, c->stream>>>(c->m, d_xy, d_val, n);
   c->launches++;
@@ -1125,6 +1144,7 @@ int shx_synth_terrain(shx_ctx* c, uint32_t seed) {
   synth_fill_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->m, sequential(c) ? 1 : 0, seed, c->d_u32);
   c->launches += 2;
   c->tracks_clean = true;
+  c->root_counts_valid = false;
   CU(cudaGetLastError());
   int rc = refresh_halo_ref(c);
   if (rc) return rc;
@@ -1142,6 +1162,7 @@ int shx_init_terrain(shx_ctx* c, int seed) {  // map::init, cellpool.h:349-409
   terrain_fill_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->m, sequential(c) ? 1 : 0, c->d_u32);
   c->launches += 2;
   c->tracks_clean = true;
+  c->root_counts_valid = false;
   CU(cudaGetLastError());
   int rc = refresh_halo_ref(c);
   if (rc) return rc;
@@ -1427,6 +1448,217 @@ int shx_peer_attach(shx_ctx* c, const shx_peer_handles* all) {
     c->pv.inbox[r] = reinterpret_cast<unsigned long long*>(p[2] + off[2]);
   }
   c->peer_attached = true;
+  return SHX_OK;
+}
+
+// ------------------------------------------------------------------------------- N3: vegetation on the device
+
+void shx_default_plant_params(shx_plant_params* pp) {
+  if (!pp) return;
+  pp->maxSize = 1.5f;        // vegetation.h:40
+  pp->growRate = 0.05f;      // :41
+  pp->maxSteep = 0.8f;       // :42
+  pp->maxDischarge = 0.3f;   // :43
+  pp->maxTreeHeight = 0.8f;  // :44
+}
+
+static int veg_ready(shx_ctx* c) {
+  if (!c) return fail(SHX_ERR_ARG, "null context");
+  if (!c->veg) return fail(SHX_ERR_MODE, "shx_veg_create has not been called on this context");
+  return SHX_OK;
+}
+
+int shx_veg_set_params(shx_ctx* c, const shx_plant_params* pp) {
+  if (!c || !pp) return fail(SHX_ERR_ARG, "null argument");
+  c->plant = PlantParams{pp->maxSize, pp->growRate, pp->maxSteep, pp->maxDischarge, pp->maxTreeHeight};
+  return SHX_OK;
+}
+
+int shx_veg_create(shx_ctx* c, size_t max_plants, const shx_plant_params* pp) {
+  if (!c) return fail(SHX_ERR_ARG, "null context");
+  if (c->veg) return fail(SHX_ERR_ARG, "the plant store exists already");
+  if (c->peer || c->m.row0 != 0 || c->m.row1 != c->size) return fail(SHX_ERR_MODE, "vegetation on the device needs a whole-map context");
+  CU(cudaSetDevice(c->cfg.device));
+  shx_plant_params def;
+  shx_default_plant_params(&def);
+  shx_veg_set_params(c, pp ? pp : &def);
+  const size_t cap = max_plants ? max_plants : std::max<size_t>(1024, c->stored_cells / 4);
+  if (cap > 0x7fffffffu) return fail(SHX_ERR_ARG, "max_plants too large");
+  const size_t slots = cap + 1, blocks = (slots + kVegBlock - 1) / kVegBlock;
+  bool ok = true;
+  for (int i = 0; i < 2; i++)
+    ok = ok && cudaMalloc((void**)&c->d_plant_pos[i], cap * sizeof(int2)) == cudaSuccess &&
+         cudaMalloc((void**)&c->d_plant_size[i], cap * sizeof(float)) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&c->d_veg_flags, slots * sizeof(unsigned)) == cudaSuccess &&
+       cudaMalloc((void**)&c->d_veg_child, slots * sizeof(int2)) == cudaSuccess &&
+       cudaMalloc((void**)&c->d_veg_grown, slots * sizeof(float)) == cudaSuccess &&
+       cudaMalloc((void**)&c->d_veg_blocks, blocks * sizeof(uint2)) == cudaSuccess &&
+       cudaMalloc((void**)&c->d_veg_totals, 8 * sizeof(unsigned)) == cudaSuccess &&
+       cudaMallocHost((void**)&c->h_veg_totals, 8 * sizeof(unsigned)) == cudaSuccess;
+  if (!ok) {
+    cudaGetLastError();
+    return fail(SHX_ERR_NOMEM, "allocation of the plant store failed");
+  }
+  c->veg_cap = cap;
+  c->veg_n = 0;
+  c->veg_cur = 0;
+  c->veg = true;
+  return SHX_OK;
+}
+
+// the integer root counts follow the fp32 rootdensity after an upload / a host push / a new terrain
+static int veg_sync_counts(shx_ctx* c) {
+  if (c->root_counts_valid) return SHX_OK;
+  veg_count_from_density_kernel<<<grid_for(c, c->stored_cells), 256, 0, c->stream>>>(c->m.rec, c->stored_cells);
+  c->launches++;
+  CU(cudaGetLastError());
+  c->root_counts_valid = true;
+  return SHX_OK;
+}
+
+static VegArgs veg_args(shx_ctx* c, uint64_t key) {
+  VegArgs a;
+  a.v = view_args(c);
+  a.pp = c->plant;
+  a.key = key;
+  a.pos = c->d_plant_pos[c->veg_cur];
+  a.size = c->d_plant_size[c->veg_cur];
+  a.n = (unsigned)c->veg_n;
+  a.pos_out = c->d_plant_pos[c->veg_cur ^ 1];
+  a.size_out = c->d_plant_size[c->veg_cur ^ 1];
+  a.cap = (unsigned)c->veg_cap;
+  a.flags = c->d_veg_flags;
+  a.child = c->d_veg_child;
+  a.grown = c->d_veg_grown;
+  a.block_counts = c->d_veg_blocks;
+  a.totals = c->d_veg_totals;
+  return a;
+}
+
+int shx_veg_grow(shx_ctx* c, uint64_t seed, uint64_t frame, shx_veg_stats* out) {
+  int rc = veg_ready(c);
+  if (rc) return rc;
+  CU(cudaSetDevice(c->cfg.device));
+  rc = veg_sync_counts(c);
+  if (rc) return rc;
+  const VegArgs a = veg_args(c, mix64(mix64(seed) + frame));
+  const unsigned slots = a.n + 1u, blocks = (slots + kVegBlock - 1) / kVegBlock;
+  veg_decide_kernel<<<blocks, kVegBlock, 0, c->stream>>>(a);
+  veg_scan_kernel<<<1, 1024, 0, c->stream>>>(a, blocks);
+  veg_apply_kernel<<<blocks, kVegBlock, 0, c->stream>>>(a);
+  veg_refresh_kernel<<<blocks, kVegBlock, 0, c->stream>>>(a);
+  c->launches += 4;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(c->h_veg_totals, c->d_veg_totals, 5 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  const unsigned* t = c->h_veg_totals;  // [0] survivors [1] born [2] died [3] refused [4] new count
+  c->veg_n = t[4];
+  c->veg_cur ^= 1;
+  if (out) {
+    out->plants = t[4];
+    out->born = t[1];
+    out->died = t[2];
+    out->refused = t[3];
+  }
+  if (t[3]) return fail(SHX_ERR_CAPACITY, "the plant list is full (max_plants of shx_veg_create): children were refused");
+  return SHX_OK;
+}
+
+int shx_veg_count(shx_ctx* c, size_t* n) {
+  int rc = veg_ready(c);
+  if (rc) return rc;
+  if (!n) return fail(SHX_ERR_ARG, "null argument");
+  *n = c->veg_n;
+  return SHX_OK;
+}
+
+int shx_veg_download(shx_ctx* c, float* xys3, size_t cap, size_t* n) {
+  int rc = veg_ready(c);
+  if (rc) return rc;
+  if (n) *n = c->veg_n;
+  if (c->veg_n > cap) return fail(SHX_ERR_CAPACITY, "buffer smaller than the plant list");
+  if (!c->veg_n) return SHX_OK;
+  if (!xys3) return fail(SHX_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->cfg.device));
+  rc = view_staging(c, c->veg_n * 3 * sizeof(float));
+  if (rc) return rc;
+  veg_export_kernel<<<grid_for(c, c->veg_n), 256, 0, c->stream>>>(c->d_plant_pos[c->veg_cur], c->d_plant_size[c->veg_cur], (unsigned)c->veg_n, c->d_view);
+  c->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(xys3, c->d_view, c->veg_n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return SHX_OK;
+}
+
+int shx_veg_upload(shx_ctx* c, const float* xys3, size_t n, int stamp_roots) {
+  int rc = veg_ready(c);
+  if (rc) return rc;
+  if (n > c->veg_cap) return fail(SHX_ERR_CAPACITY, "more plants than max_plants");
+  if (n && !xys3) return fail(SHX_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->cfg.device));
+  std::vector<int2> pos(n);
+  std::vector<float> size(n);
+  for (size_t i = 0; i < n; i++) {
+    const int x = (int)xys3[3 * i], y = (int)xys3[3 * i + 1];
+    if (x < 0 || y < 0 || x >= c->size || y >= c->size) return fail(SHX_ERR_ARG, "a plant lies outside the map");
+    pos[i] = make_int2(x, y);
+    size[i] = xys3[3 * i + 2];
+  }
+  c->veg_cur = 0;
+  c->veg_n = n;
+  if (n) {
+    CU(cudaMemcpyAsync(c->d_plant_pos[0], pos.data(), n * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_plant_size[0], size.data(), n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  }
+  if (stamp_roots && n) {
+    rc = veg_sync_counts(c);
+    if (rc) return rc;
+    // every uploaded plant as a "child" of an otherwise empty frame: apply stamps it, refresh writes the fp32 values
+    VegArgs a = veg_args(c, 0);
+    std::vector<unsigned> fl(n + 1, 2u);
+    fl[n] = 0u;
+    pos.push_back(make_int2(0, 0));
+    CU(cudaMemcpyAsync(c->d_veg_flags, fl.data(), (n + 1) * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_veg_child, pos.data(), (n + 1) * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+    const unsigned blocks = ((unsigned)n + 1u + kVegBlock - 1) / kVegBlock;
+    veg_stamp_list_kernel<<<blocks, kVegBlock, 0, c->stream>>>(a);
+    veg_refresh_kernel<<<blocks, kVegBlock, 0, c->stream>>>(a);
+    c->launches += 2;
+    CU(cudaGetLastError());
+  }
+  CU(cudaStreamSynchronize(c->stream));  // the host vectors go out of scope
+  return SHX_OK;
+}
+
+int shx_veg_tree_models(shx_ctx* c, float* dev_out16, size_t cap, size_t* n) {
+  int rc = veg_ready(c);
+  if (rc) return rc;
+  if (n) *n = c->veg_n;
+  if (c->veg_n > cap) return fail(SHX_ERR_CAPACITY, "buffer smaller than the plant list");
+  if (!c->veg_n) return SHX_OK;
+  if (!dev_out16) return fail(SHX_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->cfg.device));
+  veg_models_kernel<<<grid_for(c, c->veg_n), 256, 0, c->stream>>>(view_args(c), c->d_plant_pos[c->veg_cur], c->d_plant_size[c->veg_cur],
+                                                                   (unsigned)c->veg_n, reinterpret_cast<float4*>(dev_out16));
+  c->launches++;
+  CU(cudaGetLastError());
+  return SHX_OK;
+}
+
+int shx_veg_tree_models_download(shx_ctx* c, float* host_out16, size_t cap, size_t* n) {
+  int rc = veg_ready(c);
+  if (rc) return rc;
+  if (n) *n = c->veg_n;
+  if (c->veg_n > cap) return fail(SHX_ERR_CAPACITY, "buffer smaller than the plant list");
+  if (!c->veg_n) return SHX_OK;
+  if (!host_out16) return fail(SHX_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->cfg.device));
+  rc = view_staging(c, c->veg_n * 16 * sizeof(float));
+  if (rc) return rc;
+  rc = shx_veg_tree_models(c, c->d_view, cap, nullptr);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(host_out16, c->d_view, c->veg_n * 16 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   return SHX_OK;
 }
 

@@ -119,13 +119,15 @@ __global__ void ema_kernel(CellRec* __restrict__ rec, size_t n, float lrate, int
     f.y = keep * f.y + lrate * tx;
     f.z = keep * f.z + lrate * ty;
     reinterpret_cast<float4*>(rec + i)[0] = f;
-    if (reset) reinterpret_cast<int4*>(rec + i)[1] = make_int4(0, 0, 0, 0);
+    if (reset) reinterpret_cast<int4*>(rec + i)[1] = make_int4(0, 0, 0, t.w);  // .w: the root count of shx_veg_kernels.cuh
   }
 }
 
 __global__ void reset_tracks_kernel(CellRec* __restrict__ rec, size_t n) {  // world.h:56-61
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    reinterpret_cast<int4*>(rec + i)[1] = make_int4(0, 0, 0, 0);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int4* t = reinterpret_cast<int4*>(rec + i) + 1;
+    *t = make_int4(0, 0, 0, t->w);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -158,3 +158,5 @@ __global__ void gather_cells_kernel(const ViewArgs a, const int* __restrict__ xy
 }
 
 }  // namespace shx
+
+#include "shx_veg_kernels.cuh"

@@ -41,6 +41,15 @@ inline void params_from_statics(shx_params& p) {
   p.lrate = WorldT::lrate; p.maxdiff = WorldT::maxdiff; p.settling = WorldT::settling;
 }
 
+// Plant:: statics (vegetation.h:40-44) by name
+template <class PlantT>
+inline shx_plant_params plant_params_from_statics() {
+  shx_plant_params pp;
+  pp.maxSize = PlantT::maxSize; pp.growRate = PlantT::growRate; pp.maxSteep = PlantT::maxSteep;
+  pp.maxDischarge = PlantT::maxDischarge; pp.maxTreeHeight = PlantT::maxTreeHeight;
+  return pp;
+}
+
 class Bridge {
  public:
   // `pool` is the reference's tiled AoS cell pool (quad::cell == shx_cell, 32 bytes); it stays owned
@@ -124,6 +133,54 @@ class Bridge {
       off += n;
     }
   }
+
+  // ---- the frame loop with the vegetation on the device too (N3; single GPU): nothing but statistics crosses PCIe.
+  //   bridge.enable_device_vegetation<Plant>();                 // once, instead of keeping Vegetation::plants on the host
+  //   bridge.erode_resident<Drop, World>(quad::tilesize);       // == world.erode(quad::tilesize), SimpleHydrology.cpp:319
+  //   bridge.grow<Plant>(World::SEED, frame);                   // == Vegetation::grow(), :320 (vegetation.h:122-188)
+  //   bridge.update_vertices_device(vbo_ptr);                   // :322-324
+  //   bridge.tree_models_device(instance_ptr, capacity);        // :329-335
+  // PlantT supplies the Plant:: statics (vegetation.h:40-44).  The host pool is NOT updated by these calls;
+  // sync_pool() brings it up to date when host code wants to look at it.
+  template <class PlantT>
+  void enable_device_vegetation(size_t max_plants = 0) {
+    const shx_plant_params pp = plant_params_from_statics<PlantT>();
+    check(shx_veg_create(context(), max_plants, &pp), "shx_veg_create");
+  }
+  template <class DropT, class WorldT>
+  shx_stats erode_resident(int cycles) {
+    params_from_statics<DropT, WorldT>(params_);
+    mcheck(shx_multi_set_params(multi_, &params_), "shx_multi_set_params");
+    shx_stats st;
+    mcheck(shx_multi_erode(multi_, cycles, (uint64_t)WorldT::SEED, &st), "shx_multi_erode");
+    return st;
+  }
+  // plants_out (optional): any vector of objects constructible from a two-float position with a float `size`
+  // (Vegetation::plants) receives the list, e.g. for host code that still walks it
+  template <class PlantT, class PlantVec = std::vector<PlantT>>
+  shx_veg_stats grow(uint64_t seed, uint64_t frame, PlantVec* plants_out = nullptr) {
+    const shx_plant_params pp = plant_params_from_statics<PlantT>();
+    check(shx_veg_set_params(context(), &pp), "shx_veg_set_params");
+    shx_veg_stats st;
+    check(shx_veg_grow(context(), seed, frame, &st), "shx_veg_grow");
+    if (plants_out) {
+      std::vector<float> xys((size_t)st.plants * 3);
+      size_t n = 0;
+      check(shx_veg_download(context(), xys.data(), (size_t)st.plants, &n), "shx_veg_download");
+      plants_out->clear();
+      for (size_t i = 0; i < n; i++) {
+        plants_out->emplace_back(decltype(PlantT::pos)(xys[3 * i], xys[3 * i + 1]));
+        plants_out->back().size = xys[3 * i + 2];
+      }
+    }
+    return st;
+  }
+  size_t tree_models_device(float* dev_mat4, size_t capacity) {
+    size_t n = 0;
+    check(shx_veg_tree_models(context(), dev_mat4, capacity, &n), "shx_veg_tree_models");
+    return n;
+  }
+  void sync_pool() { mcheck(shx_multi_download(multi_, pool_, ncells_, SHX_F_ALL), "shx_multi_download"); }
 
   // sparse read-back instead of the pool download (single GPU): the records (and World::map.normal) of n cells {x, y}
   void gather(const int* xy, size_t n, shx_cell* out, float* normals3 = nullptr) {

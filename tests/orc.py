@@ -49,6 +49,17 @@ class LsWorld(C.Structure):
                 ("track", C.POINTER(C.c_int32)), ("row0", C.c_int), ("row1", C.c_int), ("align_age", C.c_int), ("max_cycles_per_launch", C.c_int), ("exclusive_cells", C.c_int), ("cur_damp", C.c_float), ("free_waits", C.c_int), ("recip_evap", C.c_int), ("steps_per_phase", C.c_int)]
 
 
+class PlantParams(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("maxSize", "growRate", "maxSteep", "maxDischarge", "maxTreeHeight")]
+
+
+class VegStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("plants", "born", "died", "refused")]
+
+
+PLANT_DTYPE = np.dtype([("x", np.int32), ("y", np.int32), ("size", np.float32)])
+
+
 def build_oracle():
     subprocess.run(["make", "-C", ORACLE_DIR, "-s"], check=True, stdout=subprocess.DEVNULL)
 
@@ -98,6 +109,12 @@ def lib():
         L.orc_ls_erode.argtypes = [C.POINTER(LsWorld), C.c_int, C.c_uint64, C.c_uint64, C.POINTER(Stats)]
         L.orc_ls_erode_spawnlist.argtypes = [C.POINTER(LsWorld), C.c_void_p, C.c_size_t, C.POINTER(Stats)]
         L.orc_synth_terrain.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
+        L.orc_default_plant_params.argtypes = [C.POINTER(PlantParams)]
+        L.orc_veg_sync_counts.argtypes = [C.POINTER(LsWorld)]
+        L.orc_veg_stamp_list.argtypes = [C.POINTER(LsWorld), C.c_void_p, C.c_size_t]
+        L.orc_veg_grow.restype = C.c_size_t
+        L.orc_veg_grow.argtypes = [C.POINTER(LsWorld), C.POINTER(PlantParams), C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t,
+                                   C.c_size_t, C.POINTER(VegStats)]
         L.orc_fill_tiled_from_planar.argtypes = [C.POINTER(Params), C.c_void_p, C.c_void_p]
         L.orc_vertex_fill.argtypes = [C.POINTER(Params), C.c_void_p, C.c_void_p]
         L.orc_view_maps.argtypes = [C.POINTER(Params), C.c_void_p, C.c_int, C.c_void_p]
@@ -247,6 +264,35 @@ class Ls:
         st = Stats()
         lib().orc_ls_erode_spawnlist(self.w, xy.ctypes.data, xy.size // 2, C.byref(st))
         return st
+
+    # ---- Vegetation::grow under the device path's schedule (orc_veg_grow)
+    def veg_create(self, max_plants, plant_params=None):
+        self.plant_params = plant_params or PlantParams()
+        if plant_params is None:
+            lib().orc_default_plant_params(C.byref(self.plant_params))
+        self.plants = np.zeros(max_plants + 1, PLANT_DTYPE)
+        self.nplants = 0
+        lib().orc_veg_sync_counts(self.w)
+
+    def veg_grow(self, seed, frame):
+        st = VegStats()
+        self.nplants = int(lib().orc_veg_grow(self.w, C.byref(self.plant_params), seed, frame, self.plants.ctypes.data, self.nplants,
+                                              self.plants.size - 1, C.byref(st)))
+        return st
+
+    def veg_upload(self, plants, stamp_roots=True):
+        plants = np.asarray(plants, np.float32).reshape(-1, 3)
+        n = plants.shape[0]
+        self.plants["x"][:n] = plants[:, 0].astype(np.int32)
+        self.plants["y"][:n] = plants[:, 1].astype(np.int32)
+        self.plants["size"][:n] = plants[:, 2]
+        self.nplants = n
+        if stamp_roots:
+            lib().orc_veg_stamp_list(self.w, self.plants.ctypes.data, n)
+
+    def veg_plants(self):
+        pl = self.plants[:self.nplants]
+        return np.stack([pl["x"].astype(np.float32), pl["y"].astype(np.float32), pl["size"]], 1)
 
     def run_drops(self, drops, trace_cap=0):
         """march explicit drop records (DROP_DTYPE) to completion, no EMA; returns (stats, trace of drop 0)"""

@@ -45,9 +45,12 @@ np.savez("%s", cells=R.cells, plants=pl)
 
 
 @pytest.mark.skipif(not (os.path.exists(BIN) and orc.have_ref(1)), reason="oracle/_ref not built (no reference tree at build time)")
-def test_coupled_erosion_and_vegetation_tracks_the_reference(tmp_path):
+@pytest.mark.parametrize("device_veg", [0, 1])
+def test_coupled_erosion_and_vegetation_tracks_the_reference(tmp_path, device_veg):
+    """device_veg = 0: the reference's unchanged Vegetation::grow on the host pool after bridge.erode;
+    device_veg = 1: bridge.erode_resident + bridge.grow<Plant> (N3), the whole frame on the device"""
     out = tmp_path / "bridge.bin"
-    r = subprocess.run([BIN, str(SEED), str(FRAMES), str(out)], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([BIN, str(SEED), str(FRAMES), str(out), "1", str(device_veg)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
     cells, plants, vertex0 = read_out(out)
     ref_npz = tmp_path / "ref.npz"
