@@ -113,3 +113,34 @@ def test_host_adaptor_compiles_against_the_c_abi(lib):
     assert os.path.exists(exe)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 2 and "usage" in r.stderr
+
+
+GL_TU = r"""
+#include <GL/gl.h>
+#define SHX_WITH_GL
+#include "simplehydrology_b200/host/shx_world.hpp"
+#include "simplehydrology_b200/host/shx_gl.hpp"
+// one frame of SimpleHydrology.cpp:322-335 with the vertex pool's VBO and the tree instance buffer mapped into CUDA
+int frame(shx::Bridge& b, unsigned vbo_name, unsigned instance_buffer_name) {
+  shx::GLBuffer vbo(vbo_name), trees(instance_buffer_name);
+  { auto m = vbo.map(); b.update_vertices_device(m.as<float>()); }
+  { auto m = trees.map(); return (int)b.tree_models_device(m.as<float>(), m.bytes / 64); }
+}
+"""
+
+
+def test_gl_interop_option_compiles(tmp_path):
+    """SHX_WITH_GL (source/vertexpool.h:155-172: the vertex pool is one GL buffer): the registration / mapping wrapper
+    compiles against the CUDA toolkit's cuda_gl_interop.h; the image has no GL headers, so the two typedefs that
+    header needs come from tests/gl_stub"""
+    cuda_inc = "/usr/local/cuda/include"
+    if not os.path.exists(os.path.join(cuda_inc, "cuda_gl_interop.h")):
+        pytest.skip("no CUDA toolkit headers")
+    src = tmp_path / "gl_tu.cpp"
+    src.write_text(GL_TU)
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    r = subprocess.run([cxx, "-std=c++17", "-Wall", "-c", str(src), "-I", ROOT, "-I", os.path.join(ROOT, "tests", "gl_stub"), "-I", cuda_inc,
+                        "-o", str(tmp_path / "gl_tu.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run(["nm", "-C", str(tmp_path / "gl_tu.o")], capture_output=True, text=True).stdout
+    assert "cudaGraphicsGLRegisterBuffer" in out and "shx_vertex_fill" in out and "shx_veg_tree_models" in out
