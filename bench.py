@@ -360,6 +360,7 @@ def run_cuda(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    launch_shape = W.launch_info()
     tm = W.timing_read()
     W.timing_enable(False)
     clocks = sampler.summary() if sampler else None
@@ -401,7 +402,9 @@ def run_cuda(args):
                 "phases_per_cycle": acc["phases"] / max(args.steps, 1),
                 "cascade_transfers_per_step": total["cascade_transfers"] / max(psteps, 1),
                 "gpu_launches": total["launches"],
-                "roofline": {"bound": "hbm", "kernel": "descend_lockstep_kernel" if rank_steps / 490 > 18944 else "descend_group_kernel",
+                "roofline": {"bound": "hbm", "kernel": {1: "descend_lockstep_kernel (one thread per drop)", 4: "descend_group_kernel (four lanes per drop)",
+                                                        8: "descend_group_kernel (eight lanes per drop)"}.get(launch_shape[2], "?"),
+                             "launch": {"ctas": launch_shape[0], "threads_per_cta": launch_shape[1], "lanes_per_drop": launch_shape[2]},
                              "achieved": achieved, "peak": hbm, "unit": "GB/s",
                              "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
                              "algorithmic_bytes_per_particle_step": BYTES_PER_STEP, "kernel_ms_per_cycle": descend_ms,

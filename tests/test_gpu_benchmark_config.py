@@ -60,7 +60,7 @@ def wait_job(jobs, name):
     return out
 
 
-@pytest.mark.parametrize("mapsize", [4, 16])
+@pytest.mark.parametrize("mapsize", [4, 8, 16])
 def test_default_launch_is_bit_exact_at_benchmark_size(mapsize, terrain16, ref_jobs):
     p = orc.default_params(mapsize)
     h = terrain16[1] if mapsize == 16 else orc.init_terrain(mapsize, 1)
@@ -75,8 +75,9 @@ def test_default_launch_is_bit_exact_at_benchmark_size(mapsize, terrain16, ref_j
                 assert getattr(st, k) == getattr(so, k), (k, epoch)
         grid, block, lanes = W.launch_info()
         h0, h1, f, t = W.download_raw()
-    # the shapes bench.py times: 8192^2 -> one thread per drop, 293 CTAs of 448; 2048^2 -> eight lanes per drop, CTAs of 256
-    assert (grid, block, lanes) == ((293, 448, 1) if mapsize == 16 else (256, 256, 8))
+    # the shapes bench.py times: 8192^2 -> one thread per drop, 293 CTAs of 448; 2048^2 -> eight lanes per drop, CTAs of
+    # 256; 4096^2 (the batch of one strip of a four-GPU run) -> four lanes per drop, CTAs of 448
+    assert (grid, block, lanes) == {16: (293, 448, 1), 8: (293, 448, 4), 4: (256, 256, 8)}[mapsize]
     assert np.array_equal(h0, ls.height_q(0)) and np.array_equal(h1, ls.height_q(1))
     assert np.array_equal(f.view(np.uint32), ls.field().view(np.uint32))
     assert np.array_equal(t[..., :3], ls.track_q()[..., :3])
