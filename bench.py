@@ -402,7 +402,7 @@ def run_cuda(args):
                 "phases_per_cycle": acc["phases"] / max(args.steps, 1),
                 "cascade_transfers_per_step": total["cascade_transfers"] / max(psteps, 1),
                 "gpu_launches": total["launches"],
-                "roofline": {"bound": "hbm", "kernel": {1: "descend_lockstep_kernel (one thread per drop)", 4: "descend_group_kernel (four lanes per drop)",
+                "roofline": {"bound": "hbm", "kernel": {1: "descend_lockstep_kernel (one thread per drop)",
                                                         8: "descend_group_kernel (eight lanes per drop)"}.get(launch_shape[2], "?"),
                              "launch": {"ctas": launch_shape[0], "threads_per_cta": launch_shape[1], "lanes_per_drop": launch_shape[2]},
                              "achieved": achieved, "peak": hbm, "unit": "GB/s",
@@ -503,6 +503,36 @@ def run_cuda(args):
             # the library reports as SHX_ERR_RANGE instead of wrapping; 4096 is the same regime inside the range)
             "default_512_erode4096": small_config(shx, torch, 1, 4096, 3, 1, l2_gbs),
             "2048_erode512": small_config(shx, torch, 4, 512, 20, 3, l2_gbs)}             # BASELINE configs[2]
+
+    # ---- weak-scaling point (N == 4 only, informational): a 16384^2 world, i.e. every GPU holds as many cells and
+    # marches as many drops per call (131 072) as the single GPU does at 8192^2 -- what the strip exchange itself costs,
+    # next to the strong-scaling headline whose limit is the latency floor of the lock step
+    if world == 4 and not peer:
+        big = strips.GpuStrip(2 * MAPSIZE, rank, world, local)
+        bex = strips.StripExchange(big, rank, world)
+        big.W.init_terrain(SEED)
+        barrier()
+        for _ in range(3):
+            bex.erode_cycle(CYCLES, SEED)
+            big.W.read_stats()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        wsteps = 0
+        barrier()
+        w0.record()
+        for _ in range(10):
+            bex.erode_cycle(CYCLES, SEED)
+            wsteps += big.W.read_stats().steps
+        w1.record()
+        barrier()
+        wt = torch.tensor([w0.elapsed_time(w1)], dtype=torch.float64, device=dev)
+        ws = torch.tensor([wsteps], dtype=torch.int64, device=dev)
+        dist.all_reduce(wt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ws)
+        big.W.close()
+        if rank == 0:
+            line["weak_scaling_point"] = {"map": "16384x16384", "n_gpus": 4, "drops_per_gpu_per_call": 2 * MAPSIZE * 2 * MAPSIZE * CYCLES // 4,
+                                          "ms_per_step": float(wt.item()) / 10, "value": float(ws.item()) / (float(wt.item()) * 1e-3),
+                                          "unit": UNIT, "note": "per-GPU work as at N = 1 on 8192^2; compare value / 4 with the N = 1 line"}
 
     # ---- e2e: the C++ host adaptor's own frame on a HOST pool (rank 0 drives all N GPUs from one thread through
     # shx_multi; the other ranks wait on the rendezvous store, not in a GPU kernel, so their devices are free)

@@ -16,12 +16,13 @@ struct LaunchShape {
   const void* kernel = nullptr;
   int block = 0;
   int cap_blocks = 0;  // co-resident CTAs (cooperative launch limit)
-  int lanes = 1;       // lanes per drop: 8 or 4 = descend_group_kernel, 1 = one thread per drop (descend_lockstep_kernel)
+  int lanes = 1;       // lanes per drop: 8 = descend_group_kernel, 1 = one thread per drop (descend_lockstep_kernel)
   size_t smem(int b) const;
   size_t drops_per_block(int b) const { return (size_t)b / (size_t)lanes; }
 };
 
 constexpr size_t kDropsPerLaunch = 131072;  // drops that march together in one launch (device-independent split)
+constexpr size_t kShapeLimit[3] = {4096, 24576, 49152};  // largest batch of launch shapes [0], [1], [2] (see shx_create)
 
 struct TimingSpan {
   int kind;  // 0 spawn, 1 descend, 2 ema, 3 pack (download), 4 device-to-host copy, 5 rootdensity push
@@ -30,10 +31,8 @@ struct TimingSpan {
 
 using namespace shx;
 
-// one thread per drop: s_B[9] + s_D[2][8] + s_S[8] x 2 words per thread; several lanes per drop: 24 words per drop
-size_t LaunchShape::smem(int b) const {
-  return lanes > 1 ? (size_t)kGroupSmemWordsPerDrop * sizeof(int32_t) * (size_t)(b / lanes) : (size_t)41 * sizeof(int32_t) * b;
-}
+// one thread per drop: s_B[9] + s_D[2][8] + s_S[8] x 2 words per thread; eight lanes per drop: 3 words per lane
+size_t LaunchShape::smem(int b) const { return (size_t)(lanes > 1 ? kGroupSmemWords : 41) * sizeof(int32_t) * b; }
 
 static thread_local std::string g_err;
 
@@ -83,7 +82,7 @@ struct shx_ctx {
   uint64_t launches = 0;
   size_t last_n = 0;        // drops of the last run still sitting in d_drops
   bool tracks_clean = true; // all track accumulators are zero (world.h:56-61 already satisfied)
-  LaunchShape shape[4];     // multi-CTA launch shapes: [0] eight lanes per drop, [1] four lanes per drop, [2] spread, [3] dense
+  LaunchShape shape[4];     // multi-CTA launch shapes: [0] eight lanes per drop, [1] CTAs of 64, [2] CTAs of 128, [3] dense (2 x 448 per SM)
   bool forced_shape = false;
   // peer mode
   bool peer = false, peer_attached = false;
@@ -350,22 +349,18 @@ int shx_create(shx_ctx** out, const shx_params* p, const shx_config* cfg_in) {
     shx_destroy(c);
     return fail(SHX_ERR_ARG, "peer mode does not take launch-shape overrides");
   }
-  // shape[0]: eight lanes per drop in CTAs of 256 threads (32 drops), four CTAs per SM: batches of up to ~19 000
-  // drops (latency regime: the reference's own sizes, the strips of an eight-GPU run); shape[1]: four lanes per
-  // drop, 2 x 448 threads per SM: up to ~33 000 drops (a 4096^2 world, the strips of a four-GPU run); one thread
-  // per drop beyond that: shape[2] "spread", CTAs of 64, and shape[3] "dense", 2 x 448 threads per SM at 72
-  // registers (throughput regime).  An explicit block_threads / variant / coop / grid_blocks in the config forces
-  // one shape for all (variant 5 = eight lanes per drop, 6 = four).
+  // Launch shapes, chosen by batch size (kShapeLimit; measured with the L2 hints on the REDs, profiles/r2_l2_hints.txt):
+  // [0] eight lanes per drop in CTAs of 256 (32 drops): up to 4 096 drops, the reference's default call; one thread
+  // per drop beyond, all with the cooperative gather at 72 registers: [1] CTAs of 64 (up to 24 576 drops: a 2048^2
+  // world, the strips of an eight-GPU run), [2] CTAs of 128 (up to 49 152: a 4096^2 world, the strips of a four-GPU
+  // run), [3] "dense", 2 x 448 threads per SM (the 8192^2 cycle).  An explicit block_threads / variant / coop /
+  // grid_blocks in the config forces one shape for all (variant 5 = eight lanes per drop).
   for (int i = 0; i < 4; i++) {
     LaunchShape& ls = c->shape[i];
     if (forced && cfg.variant == 5) {
       ls.lanes = 8;
       ls.block = cfg.block_threads > 0 ? std::min(1024, (cfg.block_threads + 31) / 32 * 32) : 256;
       ls.kernel = ls.block <= 256 ? (const void*)descend_group_kernel<256, 4> : (const void*)descend_group_kernel<1024, 1>;
-    } else if (forced && cfg.variant == 6) {
-      ls.lanes = 4;
-      ls.block = cfg.block_threads > 0 ? std::min(448, (cfg.block_threads + 31) / 32 * 32) : 448;
-      ls.kernel = ls.block <= 128 ? (const void*)descend_group_kernel<128, 7, 4> : (const void*)descend_group_kernel<448, 2, 4>;
     } else if (forced) {  // one thread per drop in one of its shapes
       ls.block = cfg.block_threads > 0 ? std::min(1024, (cfg.block_threads + 31) / 32 * 32) : 256;
       if (cfg.variant == 1) ls.block = std::min(ls.block, 512);
@@ -376,13 +371,9 @@ int shx_create(shx_ctx** out, const shx_params* p, const shx_config* cfg_in) {
       ls.lanes = 8;
       ls.block = 256;
       ls.kernel = (const void*)descend_group_kernel<256, 4>;
-    } else if (i == 1 && !peer) {
-      ls.lanes = 4;
-      ls.block = 448;
-      ls.kernel = (const void*)descend_group_kernel<448, 2, 4>;
     } else if (i <= 2) {
-      ls.block = 64;
-      ls.kernel = peer ? (const void*)descend_lockstep_kernel<128, 7, true, true> : big_kernel(64, 2, true);
+      ls.block = i == 2 ? 128 : 64;
+      ls.kernel = peer ? (const void*)descend_lockstep_kernel<128, 7, true, true> : big_kernel(ls.block, 2, true);
     } else {
       ls.block = 448;
       ls.kernel = peer ? (const void*)descend_lockstep_kernel<448, 2, true, true> : big_kernel(448, 3, true);
@@ -396,7 +387,7 @@ int shx_create(shx_ctx** out, const shx_params* p, const shx_config* cfg_in) {
     ls.cap_blocks = nb * c->sm_count;
   }
   c->forced_shape = forced;
-  if (cudaFuncSetAttribute(KERNEL_SMALL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kGroupSmemWordsPerDrop * 4 * (1024 / 8))) != cudaSuccess) {
+  if (cudaFuncSetAttribute(KERNEL_SMALL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kGroupSmemWords * 4 * 1024)) != cudaSuccess) {
     shx_destroy(c);
     return fail(SHX_ERR_CUDA, "descend kernel does not fit on this device");
   }
@@ -842,7 +833,7 @@ static int run_device_drops(shx_ctx* c, size_t n, bool trace, bool align_age = f
     // exactly ONE launch per call on every rank (even with no drops of its own): the kernels of
     // all ranks meet at every phase barrier
     if (!c->peer_attached) return fail(SHX_ERR_PEER, "shx_peer_attach has not been called");
-    const LaunchShape& ls = c->shape[(n > (size_t)c->sm_count * 256) ? 3 : 2];  // peer mode: one thread per drop
+    const LaunchShape& ls = c->shape[n <= kShapeLimit[1] ? 1 : (n <= kShapeLimit[2] ? 2 : 3)];  // peer mode: one thread per drop
     if (n > (size_t)ls.cap_blocks * ls.block) return fail(SHX_ERR_CAPACITY, "peer mode runs a call's drops in one launch");
     c->tracks_clean = false;
     DescendArgs a;
@@ -915,14 +906,12 @@ static int run_device_drops(shx_ctx* c, size_t n, bool trace, bool align_age = f
       take = left;
       a.ndrops = (unsigned)take;
       const int block = (int)((take * 8 + 31) / 32 * 32);
-      CU(launch_descend(c, (const void*)KERNEL_SMALL, 1, block, args, (size_t)kGroupSmemWordsPerDrop * 4 * (block / 8), 8));
+      CU(launch_descend(c, (const void*)KERNEL_SMALL, 1, block, args, (size_t)kGroupSmemWords * 4 * block, 8));
     } else {
-      // eight, then four lanes per drop while the whole batch is co-resident that way, one thread per drop beyond
-      int pick = left > (size_t)c->sm_count * 256 ? 3 : 2;
-      for (int i = 1; i >= 0; i--) {
-        const LaunchShape& g = c->shape[i];
-        if (g.lanes > 1 && left <= (size_t)g.cap_blocks * g.drops_per_block(g.block)) pick = i;
-      }
+      // by batch size (a constant table, not a property of the device: every shape gives the same bits anyway)
+      int pick = left <= kShapeLimit[0] ? 0 : (left <= kShapeLimit[1] ? 1 : (left <= kShapeLimit[2] ? 2 : 3));
+      if (pick == 0 && c->shape[0].lanes == 1) pick = 1;  // peer mode has no eight-lane form
+      while (pick < 3 && left > (size_t)c->shape[pick].cap_blocks * c->shape[pick].drops_per_block(c->shape[pick].block)) pick++;
       const LaunchShape& ls = c->shape[c->forced_shape ? 0 : pick];
       const int block = ls.block;
       const size_t per_block = ls.drops_per_block(block);

@@ -1,4 +1,4 @@
-// K3 for batches that cannot fill the GPU with one thread per drop: descend_group_kernel, EIGHT (or four) LANES PER DROP
+// K3 for small batches (a few thousand drops: the reference's default call): descend_group_kernel, EIGHT LANES PER DROP
 // (included by shx_kernels.cuh, which holds the shared pieces: the map view, DescendArgs, the grid barrier, claim
 // keys, and the one-thread-per-drop kernel descend_lockstep_kernel used for dense batches and peer mode).
 //
@@ -27,44 +27,34 @@ __device__ __forceinline__ int neighbour_offset(int j, int size) {  // cell inde
   return (kx - 1) * size + (k - 3 * kx - 1);
 }
 
-// Dynamic shared memory per GROUP: eight int2 {height, neighbour index} of the cascade order and eight ints of the
-// heights handed back in natural order = 24 words, i.e. 3 words per lane with eight lanes per drop, 6 with four.
+// Dynamic shared memory per lane: one int2 {height, neighbour index} of the group's cascade order and one int of the
+// heights handed back in natural order.
 constexpr int kGroupSmemWords = 3;
-constexpr int kGroupSmemWordsPerDrop = 24;
 
-// L lanes per drop, L = 8 or 4.  Lane l of a group owns the neighbours j = s*L + l, s = 0 .. 8/L - 1 ("slots"): with
-// eight lanes one neighbour each, with four lanes two (l and l + 4).  Four lanes per drop double the batch that is
-// co-resident this way (one 8192^2 strip of four, a 4096^2 world) at the price of a somewhat longer chain.
-template <int kMaxThreads, int kMinBlocks, int L = 8>
+template <int kMaxThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_group_kernel(const __grid_constant__ DescendArgs a) {
-  static_assert(L == 8 || L == 4, "lanes per drop");
-  constexpr int S = 8 / L;  // neighbours per lane
   extern __shared__ int32_t s_mem[];
   __shared__ unsigned s_total;
   __shared__ unsigned s_hi[2];  // grid barrier bookkeeping, touched by thread 0 only
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
   if (tid == 0) s_hi[0] = s_hi[1] = 0u;
-  const int l = lane & (L - 1), gl = lane & ~(L - 1);  // lane within the group, first lane of the group
-  const unsigned gmask = (L == 8 ? 0xFFu : 0xFu) << gl;
-  const int grp = tid / L;
-  int2* const s_sorted = reinterpret_cast<int2*>(s_mem) + grp * 8;        // [8] per group
-  int* const s_back = s_mem + 2 * 8 * (nt / L) + grp * 8;                 // [8] per group
+  const int j = lane & 7, gl = lane & ~7;  // neighbour index of this lane, first lane of its group
+  const unsigned gmask = 0xFFu << gl;
+  int2* const s_sorted = reinterpret_cast<int2*>(s_mem) + (tid & ~7);  // [8] per group
+  int* const s_back = s_mem + 2 * nt + (tid & ~7);                      // [8] per group
   const int size = a.m.size, xlo = a.m.xlo;
   int* const H = reinterpret_cast<int*>(a.m.hq);
   CellRec* const REC = a.m.rec;
-  int my_off[S];
-  unsigned my_need[S];  // which sides of the map this lane's neighbour needs (edge flags, see below)
-#pragma unroll
-  for (int s = 0; s < S; s++) {
-    const int j = s * L + l;
-    my_off[s] = neighbour_offset(j, size);
+  const int my_off = neighbour_offset(j, size);
+  const unsigned my_need = [&] {  // which sides of the map this lane's neighbour needs (edge flags, see below)
     const int k = j + (j >> 2), dx = k / 3 - 1, dy = k % 3 - 1;
-    my_need[s] = (dx < 0 ? 1u : 0u) | (dx > 0 ? 2u : 0u) | (dy < 0 ? 4u : 0u) | (dy > 0 ? 8u : 0u);
-  }
-  const unsigned gdrop = blockIdx.x * (unsigned)(nt / L) + (unsigned)grp;
-  const bool leader = l == 0;
+    return (dx < 0 ? 1u : 0u) | (dx > 0 ? 2u : 0u) | (dy < 0 ? 4u : 0u) | (dy > 0 ? 8u : 0u);
+  }();
+  const bool my_diag = (0xA5u >> j) & 1u;
+  const unsigned gdrop = blockIdx.x * (unsigned)(nt >> 3) + (unsigned)(tid >> 3);
+  const bool leader = j == 0;
 
-  DropRegs d;  // replicated in the lanes of the group
+  DropRegs d;  // replicated in the eight lanes of the group
   d.px = d.py = d.sx = d.sy = d.vol = d.sed = 0.0f;
   d.age = 0;
   d.flags = 0;
@@ -79,9 +69,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_group_kernel(
   alive = alive && !asleep;
   unsigned mykey = 0u;     // the key this drop claimed its cell with for the coming phase
   int pc = 0, dC_prev = 0;  // centre cell and centre delta of the previous phase (owed to the other plane)
-  int pend_cell[S], pend_val[S];  // this lane's cascade transfers of the previous phase (likewise)
-#pragma unroll
-  for (int s = 0; s < S; s++) pend_cell[s] = pend_val[s] = 0;
+  int pend_cell = 0, pend_val = 0;  // this lane's cascade transfer of the previous phase (likewise)
   unsigned steps = 0, transfers = 0;
   long long fx_eroded = 0, fx_inflation = 0;
   int tn = 0;
@@ -95,16 +83,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_group_kernel(
   };
   auto claim = [&](int cell, int word, unsigned phase_tag) {  // claim `cell` for the phase with this tag
     mykey = claim_key(a.claim_epoch, phase_tag, d);
-    if (leader) atomicMax(reinterpret_cast<unsigned*>(H + 4 * (size_t)cell + word + 1), mykey);
-  };
-  // neighbour j of this group's block: the value `v[s]` held by lane j % L in slot j / L
-  auto from_owner = [&](const int (&v)[S], int j) {
-    int r = __shfl_sync(gmask, v[0], gl + (j & (L - 1)));
-    if (S > 1) {
-      const int r1 = __shfl_sync(gmask, v[S - 1], gl + (j & (L - 1)));
-      r = (j >= L) ? r1 : r;
-    }
-    return r;
+    if (leader) red_claim(reinterpret_cast<unsigned*>(H + 4 * (size_t)cell + word + 1), mykey);
   };
 
   if (alive) claim(cell_of(d.px, d.py), 0, 1u);  // every drop that is awake in phase 0 claims its cell (tag 1, parity 0)
@@ -123,41 +102,29 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_group_kernel(
     const int cidx = (ix - xlo) * size + iy;
     // cellpool.h:413-419 for the block: which of the four sides exist
     const unsigned ef = (ix > 0 ? 1u : 0u) | (ix < size - 1 ? 2u : 0u) | (iy > 0 ? 4u : 0u) | (iy < size - 1 ? 8u : 0u);
-    bool valid[S];  // this lane's neighbour cells exist
-#pragma unroll
-    for (int s = 0; s < S; s++) valid[s] = (ef & my_need[s]) == my_need[s];
+    const bool valid = (ef & my_need) == my_need;  // this lane's neighbour cell exists
 
-    // gather: one {height, claim} pair per lane and slot, the centre pair and the cell record once per group
-    int2 nb[S], cc = make_int2(0, 0);
-#pragma unroll
-    for (int s = 0; s < S; s++) nb[s] = make_int2(0, 0);
+    // gather: one {height, claim} pair per lane, the centre pair and the cell record once per group
+    int2 nb = make_int2(0, 0), cc = make_int2(0, 0);
     float4 fld = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (alive) {
-#pragma unroll
-      for (int s = 0; s < S; s++)
-        if (valid[s]) nb[s] = __ldcg(reinterpret_cast<const int2*>(H + 4 * (size_t)(cidx + my_off[s]) + rw));
+      if (valid) nb = __ldcg(reinterpret_cast<const int2*>(H + 4 * (size_t)(cidx + my_off) + rw));
       cc = __ldcg(reinterpret_cast<const int2*>(H + 4 * (size_t)cidx + rw));
       fld = __ldg(reinterpret_cast<const float4*>(REC + cidx));
     }
     // "catch-up": the previous phase's deltas for the plane that was being read then
-#pragma unroll
-    for (int s = 0; s < S; s++)
-      if (pend_val[s]) {
-        atomicAdd(H + 4 * (size_t)pend_cell[s] + ww, pend_val[s]);
-        pend_val[s] = 0;
-      }
+    if (pend_val) {
+      red_height(H + 4 * (size_t)pend_cell + ww, pend_val);
+      pend_val = 0;
+    }
     if (dC_prev) {
-      if (leader) atomicAdd(H + 4 * (size_t)pc + ww, dC_prev);
+      if (leader) red_height(H + 4 * (size_t)pc + ww, dC_prev);
       dC_prev = 0;
     }
     const int hC = cc.x;
     // how many of the eight cells around hold a higher key this phase
-    int crowded = 0;
-#pragma unroll
-    for (int s = 0; s < S; s++) {
-      const unsigned crowd = __ballot_sync(0xffffffffu, (unsigned)nb[s].y > mykey);
-      crowded += __popc((crowd >> gl) & (L == 8 ? 0xFFu : 0xFu));
-    }
+    const unsigned crowd = __ballot_sync(0xffffffffu, (unsigned)nb.y > mykey);
+    const int crowded = __popc((crowd >> gl) & 0xFFu);
     // whose turn is it on this cell?  (claimed during the previous phase, complete since its barrier)
     const bool turn = alive && (unsigned)cc.y == mykey;
 
@@ -165,7 +132,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_group_kernel(
       if (wait_one_phase(d, a)) {  // expired in the queue: the sediment stays here (water.h:74-77)
         const int q = h_quantize(d.sed);
         if (leader) {
-          if (q) atomicAdd(H + 4 * (size_t)cidx + ww, q);
+          if (q) red_height(H + 4 * (size_t)cidx + ww, q);
           atomicMax(&a.bar->max_steps, phase + 1u);
           stat_add(a.stats, ST_TERM_AGE, 1ull);
           stat_add(a.stats, ST_FX_DEPOSITED, (unsigned long long)(long long)q);
@@ -187,94 +154,65 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_group_kernel(
       const float damp = __int_as_float((127 - crowded) << 23);
       steps++;
       d.flags &= ~(7 << kWaitedShift);
-      int hN[S];  // this lane's neighbours (0 if the cell does not exist)
-#pragma unroll
-      for (int s = 0; s < S; s++) hN[s] = nb[s].x;
+      int hN = nb.x;  // this lane's neighbour (0 if the cell does not exist)
       int Bc = hC;
 
       if (d.flags & SHX_DROP_CASCADE) {  // World::cascade of the previous call, world.h:90-168
         d.flags &= ~SHX_DROP_CASCADE;
+        const float h = h_to_float(hN);
+        const float lim = above_tenth(h) ? (my_diag ? a.P.lim_diag : a.P.lim_axis) : 0.0f;  // world.h:143-148
         // The centre only changes through a transfer: if no neighbour exceeds its allowance against the untouched
         // centre, nothing fires at all (excess > 0 implies diff != 0 because lim >= 0).
-        bool fire = false;
-        float hh[S];
-#pragma unroll
-        for (int s = 0; s < S; s++) {
-          const int j = s * L + l;
-          const float h = h_to_float(hN[s]);
-          const bool diag = (0xA5u >> j) & 1u;
-          const float lim = above_tenth(h) ? (diag ? a.P.lim_diag : a.P.lim_axis) : 0.0f;  // world.h:143-148
-          fire |= valid[s] && (fabsf(h_to_float(Bc) - h) - lim) > 0.0f;
-          hh[s] = valid[s] ? h : __int_as_float(0x7f800000);  // missing cells sort last
-        }
+        const bool fire = valid && (fabsf(h_to_float(Bc) - h) - lim) > 0.0f;
         if (__ballot_sync(gmask, fire)) {
           // world.h:129-131 ascending by height; libstdc++ sorts <= 16 elements by insertion, i.e. stably: i comes
-          // before j iff h_i < h_j, or h_i == h_j and i < j.
-          int rank[S];
+          // before j iff h_i < h_j, or h_i == h_j and i < j.  Missing cells sort last.
+          const float hh = valid ? h : __int_as_float(0x7f800000);
+          int rank = 0;
 #pragma unroll
-          for (int s = 0; s < S; s++) rank[s] = 0;
-#pragma unroll
-          for (int t = 0; t < S; t++)
-#pragma unroll
-            for (int i = 0; i < L; i++) {
-              const float hi = __shfl_sync(gmask, hh[t], gl + i);  // neighbour t*L + i
-#pragma unroll
-              for (int s = 0; s < S; s++) rank[s] += (hi < hh[s] || (hi == hh[s] && t * L + i < s * L + l)) ? 1 : 0;
-            }
-#pragma unroll
-          for (int s = 0; s < S; s++) s_sorted[rank[s]] = make_int2(hN[s], valid[s] ? s * L + l : 8);
-          __syncwarp(gmask);
-          int2 e[S];  // lane l now holds the neighbours of rank s*L + l
-          float hn[S], lim_n[S];
-#pragma unroll
-          for (int s = 0; s < S; s++) {
-            e[s] = s_sorted[s * L + l];
-            hn[s] = h_to_float(e[s].x);
-            lim_n[s] = above_tenth(hn[s]) ? (((0xA5u >> e[s].y) & 1u) ? a.P.lim_diag : a.P.lim_axis) : 0.0f;
+          for (int i = 0; i < 8; i++) {
+            const float hi = __shfl_sync(gmask, hh, gl + i);
+            rank += (hi < hh || (hi == hh && i < j)) ? 1 : 0;
           }
-          int my_s[S];
-          bool my_fired[S];  // a transfer that rounds to zero height units still counts as one (world.h:154)
+          s_sorted[rank] = make_int2(hN, valid ? j : 8);
+          __syncwarp(gmask);
+          const int2 e = s_sorted[j];  // lane r now holds the neighbour of rank r
+          const int jn = e.y;
+          const float hn = h_to_float(e.x);
+          const float lim_n = above_tenth(hn) ? (((0xA5u >> jn) & 1u) ? a.P.lim_diag : a.P.lim_axis) : 0.0f;
+          int my_s = 0;
+          bool my_fired = false;  // a transfer that rounds to zero height units still counts as one (world.h:154)
 #pragma unroll
-          for (int s = 0; s < S; s++) { my_s[s] = 0; my_fired[s] = false; }
-#pragma unroll
-          for (int r = 0; r < 8; r++) {  // the Gauss-Seidel chain: the holder of rank r moves, everybody follows the centre
-            const int s = r / L;  // compile-time after unrolling
-            const float diff = h_to_float(Bc) - hn[s];  // world.h:138: centre re-read, neighbour snapshot
-            const float excess = fabsf(diff) - lim_n[s];
-            const bool fires = e[s].y < 8 && diff != 0.0f && excess > 0.0f;
-            int sft = 0;
+          for (int r = 0; r < 8; r++) {  // the Gauss-Seidel chain: lane r moves, everybody follows the centre
+            const float diff = h_to_float(Bc) - hn;  // world.h:138: centre re-read, neighbour snapshot
+            const float excess = fabsf(diff) - lim_n;
+            const bool fires = jn < 8 && diff != 0.0f && excess > 0.0f;
+            int s = 0;
             if (fires) {
               const int t = h_quantize((a.P.settling * damp) * excess / 2.0f);  // world.h:154
-              sft = diff > 0.0f ? t : -t;                                       // world.h:157-164
+              s = diff > 0.0f ? t : -t;                                         // world.h:157-164
             }
-            if (l == (r & (L - 1))) {
-              my_s[s] = sft;
-              my_fired[s] = fires;
+            if (j == r) {
+              my_s = s;
+              my_fired = fires;
             }
-            Bc -= __shfl_sync(gmask, sft, gl + (r & (L - 1)));
+            Bc -= __shfl_sync(gmask, s, gl + r);
           }
-          unsigned nfired = 0;
-#pragma unroll
-          for (int s = 0; s < S; s++) {
-            const int jn = e[s].y;
-            if (jn < 8) s_back[jn] = e[s].x + my_s[s];
-            if (my_s[s]) {
-              pend_cell[s] = cidx + neighbour_offset(jn, size);
-              pend_val[s] = my_s[s];
-              atomicAdd(H + 4 * (size_t)pend_cell[s] + ww, my_s[s]);
-            }
-            nfired += (unsigned)__popc(__ballot_sync(gmask, my_fired[s]));
+          if (jn < 8) s_back[jn] = e.x + my_s;
+          if (my_s) {
+            pend_cell = cidx + neighbour_offset(jn, size);
+            pend_val = my_s;
+            red_height(H + 4 * (size_t)pend_cell + ww, my_s);
           }
-          transfers += nfired;
+          transfers += (unsigned)__popc(__ballot_sync(gmask, my_fired));
           __syncwarp(gmask);
-#pragma unroll
-          for (int s = 0; s < S; s++) hN[s] = valid[s] ? s_back[s * L + l] : 0;
+          hN = valid ? s_back[j] : 0;
         }
       }
 
       const float hc = h_to_float(Bc);
-      const int q_xm = from_owner(hN, 1), q_xp = from_owner(hN, 6);
-      const int q_ym = from_owner(hN, 3), q_yp = from_owner(hN, 4);
+      const int q_xm = __shfl_sync(gmask, hN, gl + 1), q_xp = __shfl_sync(gmask, hN, gl + 6);
+      const int q_ym = __shfl_sync(gmask, hN, gl + 3), q_yp = __shfl_sync(gmask, hN, gl + 4);
       const float hxm = (ef & 1u) ? h_to_float(q_xm) : 0.0f, hxp = (ef & 2u) ? h_to_float(q_xp) : 0.0f;
       const float hym = (ef & 4u) ? h_to_float(q_ym) : 0.0f, hyp = (ef & 8u) ? h_to_float(q_yp) : 0.0f;
       const MoveResult mv = move_math(hc, hxm, hxp, hym, hyp, inb9_from_valid8(valid8_from_edges(ef)), d, fld, a.P, size);
@@ -300,16 +238,16 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_group_kernel(
           const int ddx = nix - ix, ddy = niy - iy;
           if (ddx >= -1 && ddx <= 1 && ddy >= -1 && ddy <= 1) {
             const int k = (ddx + 1) * 3 + (ddy + 1);
-            hv = from_owner(hN, k > 4 ? k - 1 : k & 7);
+            hv = __shfl_sync(gmask, hN, gl + (k > 4 ? k - 1 : k & 7));
             if (k == 4) hv = Bc;  // a drop without speed stays where it is
           } else {
             hv = __ldcg(H + 4 * (size_t)ncidx + rw);
           }
         }
         const float cap = 1.0f + a.P.entrainment * shx_erff(0.4f * fld.x);  // water.h:127, cellpool.h:242-244
-        if (l < 3) {  // water.h:115-117: lanes 0..2 add the three track amounts
-          const float tv = l == 0 ? mv.t_d : (l == 1 ? mv.t_mx : mv.t_my);
-          atomicAdd(&REC[cidx].track_d + l, t_quantize(tv));
+        if (j < 3) {  // water.h:115-117: lanes 0..2 add the three track amounts
+          const float tv = j == 0 ? mv.t_d : (j == 1 ? mv.t_mx : mv.t_my);
+          red_track32(&REC[cidx].track_d + j, t_quantize(tv));
         }
         const float h2 = mv.oob ? oob_h2(hc) : h_to_float(hv);  // water.h:121-124
         float carried;
@@ -346,15 +284,12 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_group_kernel(
         }
         trace_row();
       }
-      if (l == 3 && dC) atomicAdd(H + 4 * (size_t)cidx + ww, dC);
+      if (j == 3 && dC) red_height(H + 4 * (size_t)cidx + ww, dC);
       dC_prev = dC;
       pc = cidx;
     }
 
-    int pending = dC_prev;
-#pragma unroll
-    for (int s = 0; s < S; s++) pending |= pend_val[s];
-    const unsigned block_sum = (unsigned)__syncthreads_count(alive || asleep || pending);
+    const unsigned block_sum = (unsigned)__syncthreads_count(alive || asleep || (dC_prev | pend_val));
     if (grid_barrier_sum(a.bar, phase + 1u, block_sum, &s_total, s_hi[0], s_hi[1]) == 0u) break;
     if (phase + 3u >= kMaxPhases) {  // the claim tag would wrap: give up (the host reports SHX_ERR_RANGE)
       if (blockIdx.x == 0 && tid == 0) atomicOr(a.abort_flag, 2);

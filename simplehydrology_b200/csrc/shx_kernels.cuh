@@ -288,6 +288,36 @@ __device__ __forceinline__ bool wait_one_phase(DropRegs& d, const DescendArgs& a
   return (float)d.age > a.P.maxAge;
 }
 
+// L2 eviction-priority hints on the REDs (round 2; measured at 8192^2: 11.4 -> 8.9 ms per cycle).  A drop's next 3x3
+// block overlaps its current one and every height add is repeated on the other plane one phase later (catch-up), so
+// the sector a height RED or a claim lands in is wanted again within a phase or two: those carry evict_last.  A cell
+// record is read and added to in ONE phase and not again until another drop passes: the track REDs carry evict_first.
+// Without the hints ~38 MB stream through L2 per phase and the sectors are gone when they are needed again.  The same
+// hints on the LOADS do not help (height gathers evict_last: +1 %, record loads evict_first: +6 %); profiles/
+// r2_l2_hints.txt holds the sweep.
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_stream() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void red_height(int* p, int v) {
+  asm volatile("red.global.add.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(l2_policy_keep()) : "memory");
+}
+__device__ __forceinline__ void red_claim(unsigned* p, unsigned v) {
+  asm volatile("red.global.max.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(l2_policy_keep()) : "memory");
+}
+__device__ __forceinline__ void red_track32(int* p, int v) {
+  asm volatile("red.global.add.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(l2_policy_stream()) : "memory");
+}
+__device__ __forceinline__ void red_track64(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.global.add.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(l2_policy_stream()) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // K3: batched lock-step descend.  One thread per drop, drop state in registers, the 3x3 block of
 // the current phase in shared memory.  Phase p:
@@ -350,18 +380,22 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
   auto claim_at = [&](int x, int y) -> unsigned* { return reinterpret_cast<unsigned*>(h_at(x, y)) + 1; };
   auto claim_max = [&](unsigned* p, unsigned key, int x) {
     if (kPeer && (x >> a.pv.shift) != a.pv.rank) { atomicMax_system(p, key); s_remote = 1u; }
-    else atomicMax(p, key);
+    else red_claim(p, key);
   };
   // Integer adds.  Peer mode: every add into a strip is performed by the L2 of the GPU that holds it;
   // the owner uses plain device-scope REDs, the others system-scope ones over NVLink, and a CTA
   // that sent anything off-device raises s_remote so that its arrival fence is system scope.
-  auto add32 = [&](int* p, int v, int x) {
+  auto add32 = [&](int* p, int v, int x) {  // heights
     if (kPeer && (x >> a.pv.shift) != a.pv.rank) { atomicAdd_system(p, v); s_remote = 1u; }
-    else atomicAdd(p, v);
+    else red_height(p, v);
   };
-  auto add64 = [&](unsigned long long* p, unsigned long long v, int x) {
+  auto track32 = [&](int* p, int v, int x) {
     if (kPeer && (x >> a.pv.shift) != a.pv.rank) { atomicAdd_system(p, v); s_remote = 1u; }
-    else atomicAdd(p, v);
+    else red_track32(p, v);
+  };
+  auto add64 = [&](unsigned long long* p, unsigned long long v, int x) {  // tracks
+    if (kPeer && (x >> a.pv.shift) != a.pv.rank) { atomicAdd_system(p, v); s_remote = 1u; }
+    else red_track64(p, v);
   };
 
   DropRegs d;
@@ -637,7 +671,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_lockstep_kern
           const unsigned long long packed = ((unsigned long long)(unsigned)t_quantize(mv.t_mx) << 32) |
                                             (unsigned long long)(unsigned)t_quantize(mv.t_d);
           add64(reinterpret_cast<unsigned long long*>(&rec->track_d), packed, ix);
-          add32(&rec->track_my, t_quantize(mv.t_my), ix);
+          track32(&rec->track_my, t_quantize(mv.t_my), ix);
         }
         const float h2 = mv.oob ? oob_h2(hc) : h_to_float(hv);  // water.h:121-124
         float carried;

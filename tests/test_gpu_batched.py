@@ -72,14 +72,13 @@ def test_single_drop_trace_and_deposits_bit_exact(init_cells):
                                 dict(variant=2, coop=1), dict(variant=3, coop=1), dict(block_threads=1024, coop=1),
                                 dict(block_threads=96, variant=2, coop=1, grid_blocks=3),
                                 dict(variant=5), dict(variant=5, block_threads=64), dict(variant=5, block_threads=1024),
-                                dict(variant=5, block_threads=256, grid_blocks=9),
-                                dict(variant=6), dict(variant=6, block_threads=128), dict(variant=6, block_threads=64, grid_blocks=13)])
+                                dict(variant=5, block_threads=256, grid_blocks=9)])
 def test_erode_cycles_bit_exact_for_every_launch_shape(golden, init_cells, kw):
     """kw: default = the library's own choice; the others force CTA size, register budget, the
-    warp-cooperative gather, the eight- and four-lanes-per-drop kernels (variants 5, 6) and, with grid_blocks,
-    sub-batches (7 x 32 = 224 / 3 x 96 = 288 / 9 x 32 = 288 / 13 x 16 = 208 drops)."""
+    warp-cooperative gather, the eight-lanes-per-drop kernel (variant 5) and, with grid_blocks, sub-batches
+    (7 x 32 = 224 / 3 x 96 = 288 / 9 x 32 = 288 drops)."""
     W, ls = make_world(init_cells, orc.default_params(1), **kw)
-    cap = kw["grid_blocks"] * kw["block_threads"] // {5: 8, 6: 4}.get(kw.get("variant"), 1) if kw.get("grid_blocks") else None
+    cap = kw["grid_blocks"] * kw["block_threads"] // (8 if kw.get("variant") == 5 else 1) if kw.get("grid_blocks") else None
     for c, xy in enumerate(golden["spawn_lists"][:3]):
         st = W.erode_spawnlist(xy)
         if cap is None:

@@ -75,9 +75,10 @@ def test_default_launch_is_bit_exact_at_benchmark_size(mapsize, terrain16, ref_j
                 assert getattr(st, k) == getattr(so, k), (k, epoch)
         grid, block, lanes = W.launch_info()
         h0, h1, f, t = W.download_raw()
-    # the shapes bench.py times: 8192^2 -> one thread per drop, 293 CTAs of 448; 2048^2 -> eight lanes per drop, CTAs of
-    # 256; 4096^2 (the batch of one strip of a four-GPU run) -> four lanes per drop, CTAs of 448
-    assert (grid, block, lanes) == {16: (293, 448, 1), 8: (293, 448, 4), 4: (256, 256, 8)}[mapsize]
+    # the shapes bench.py times, all one thread per drop: 8192^2 -> 293 CTAs of 448; 4096^2 (the batch of one strip of
+    # a four-GPU run) -> 256 CTAs of 128; 2048^2 -> 128 CTAs of 64.  (Eight lanes per drop serve batches of up to 4 096
+    # drops: tests/test_gpu_batched.py and the 512^2 tests.)
+    assert (grid, block, lanes) == {16: (293, 448, 1), 8: (256, 128, 1), 4: (128, 64, 1)}[mapsize]
     assert np.array_equal(h0, ls.height_q(0)) and np.array_equal(h1, ls.height_q(1))
     assert np.array_equal(f.view(np.uint32), ls.field().view(np.uint32))
     assert np.array_equal(t[..., :3], ls.track_q()[..., :3])
@@ -105,7 +106,7 @@ def test_check3_full_density_2048_over_40_calls(ref_jobs):
             if c + 1 in (20, 40):
                 cells = W.download()
                 got[c + 1] = (cells["height"].copy(), cells["discharge"].copy())
-        assert W.launch_info()[2] == 8
+        assert W.launch_info() == (128, 64, 1)
     ref, shuf = wait_job(ref_jobs, "m4_ref"), wait_job(ref_jobs, "m4_shuf")
     for cp in (20, 40):
         rh, rd = np.load(f"{ref}_h{cp}.npy"), np.load(f"{ref}_d{cp}.npy")

@@ -9,10 +9,10 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 # one --set full capture per descend kernel in the configuration that uses it
 ncu --set full --clock-control none --import-source on -k regex:descend_lockstep -s 2 -c 1 -f -o $O/r2_dense_8192 \
     python tools/tune_descend.py 16 0:0:0 > $O/r2_ncu_dense.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:descend_group -s 2 -c 1 -f -o $O/r2_quad_4096 \
-    python tools/tune_descend.py 8 0:0:0 > $O/r2_ncu_quad.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:descend_group -s 2 -c 1 -f -o $O/r2_group_2048 \
-    python tools/tune_descend.py 4 0:0:0 > $O/r2_ncu_group2048.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:descend_lockstep -s 2 -c 1 -f -o $O/r2_mid_4096 \
+    python tools/tune_descend.py 8 0:0:0 > $O/r2_ncu_mid4096.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:descend_lockstep -s 2 -c 1 -f -o $O/r2_small_2048 \
+    python tools/tune_descend.py 4 0:0:0 > $O/r2_ncu_small2048.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:descend_group -s 2 -c 1 -f -o $O/r2_group_512 \
     python tools/tune_descend.py 1 0:0:0 > $O/r2_ncu_group512.log 2>&1
 ncu --set full --clock-control none -k regex:ema_kernel -s 2 -c 1 -f -o $O/r2_ema \

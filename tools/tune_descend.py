@@ -37,5 +37,6 @@ if __name__ == "__main__":
     ms = int(sys.argv[1])
     cfgs = sys.argv[2:] or ["256:0:0"]
     for c in cfgs:
-        b, v, g, co, cy = (int(x) for x in (c.split(":") + ["0", "512"])[:5]) if c.count(":") < 4 else (int(x) for x in c.split(":"))
-        run(ms, b, v, g, co, cycles=cy)
+        f = [int(x) for x in c.split(":")]
+        f += [0, 0, 0, 0, 512][len(f):]  # block:variant:grid:coop:cycles
+        run(ms, f[0], f[1], f[2], f[3], cycles=f[4])
