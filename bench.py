@@ -532,7 +532,8 @@ def run_cuda(args):
         if rank == 0:
             line["weak_scaling_point"] = {"map": "16384x16384", "n_gpus": 4, "drops_per_gpu_per_call": 2 * MAPSIZE * 2 * MAPSIZE * CYCLES // 4,
                                           "ms_per_step": float(wt.item()) / 10, "value": float(ws.item()) / (float(wt.item()) * 1e-3),
-                                          "unit": UNIT, "note": "per-GPU work as at N = 1 on 8192^2; compare value / 4 with the N = 1 line"}
+                                          "unit": UNIT, "note": "per-GPU cells and spawned drops as at N = 1 on 8192^2; compare value / 4 with the N = 1 line. A strip's batch is its 131 072 spawned drops "
+                                                  "PLUS the drops its neighbours handed over, and a launch holds at most 131 072: every call pays a second, latency-bound launch"}
 
     # ---- e2e: the C++ host adaptor's own frame on a HOST pool (rank 0 drives all N GPUs from one thread through
     # shx_multi; the other ranks wait on the rendezvous store, not in a GPU kernel, so their devices are free)
