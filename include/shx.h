@@ -85,7 +85,7 @@ enum {
 };
 
 /* Counters of one call.  fx_* are exact integers: heights in Q5.26 (2^-26 units),
- * sediment sums in Q31.32.  Ledger identity (tests/test_ledger.py):
+ * sediment sums in Q31.32.  Ledger identity (tests/test_gpu_reference_parity.py::test_check2_mass_ledger):
  *   sum(height_after) - sum(height_before) == fx_deposited - fx_eroded   (exactly, in Q5.26) */
 typedef struct {
   uint64_t spawned, rejected, steps, term_age, term_vol, term_oob, cascade_transfers, phases;

@@ -4,7 +4,7 @@
 // every fp32 operation below is a single correctly-rounded IEEE operation in the order
 // written.  That is what makes (a) the sequential mode reproduce the reference's g++ -O2
 // arithmetic and (b) the batched mode comparable bit for bit with the CPU lock-step
-// oracle (tests/test_parity_batched_gpu.py).
+// oracle (tests/test_gpu_batched.py).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
