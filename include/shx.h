@@ -192,6 +192,14 @@ int shx_host_unregister(void* ptr);
 int shx_upload(shx_ctx* c, const shx_cell* pool, size_t ncells);
 int shx_download(shx_ctx* c, shx_cell* pool, size_t ncells, unsigned field_mask);
 int shx_download_async(shx_ctx* c, shx_cell* pool, size_t ncells, unsigned field_mask);
+/* {height, discharge, momentumx, momentumy} only -- the first 16 bytes of every owned record, i.e. what updatenode,
+ * the texture builders and vegetation.h read after World::erode -- in half the PCIe bytes: a dense 16-byte stream is
+ * copied into pinned chunks and scattered into the pool by `nthreads` host threads (0 = all) as it lands.  The
+ * *_track words and rootdensity of the pool are left untouched.  Blocks.  Faster or slower than shx_download
+ * depending on the host's memory bandwidth (every record costs the host a read-for-ownership of its cache line):
+ * on this project's B200 boxes (16 host cores) 52.3 ms against 51.7 per 8192^2 frame, i.e. no gain, so shx::Bridge
+ * keeps whole records by default and offers this as DownloadMode kCompact / kAuto. */
+int shx_download_compact(shx_ctx* c, shx_cell* pool, size_t ncells, int nthreads);
 
 /* == World::erode(cycles), world.h:54-88: reset tracks, `cycles` drops per node, EMA.
  * rand() is replaced by a counter-based hash keyed (seed, call counter, node, i). */
@@ -206,6 +214,7 @@ typedef struct {
   double pack_ms;  /* shx_download: device layout -> tiled AoS staging tiles (sum over tiles) */
   double d2h_ms;   /* shx_download: the device-to-host copies on the copy stream (sum over tiles; overlaps pack_ms) */
   double push_ms;  /* shx_add/set_rootdensity: host-to-device copy + kernel */
+  double scatter_ms; /* shx_download_compact: HOST time from the first chunk's arrival to the last record scattered */
 } shx_timing;
 /* shape of the last descend launch of this context: CTAs, threads per CTA, lanes per drop (1 = one thread per drop,
  * the dense / spread shapes; 8 = eight lanes per drop).  Results never depend on it; tests assert which kernel ran. */

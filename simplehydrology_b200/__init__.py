@@ -76,7 +76,8 @@ class VegStats(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("spawn_ms", C.c_double), ("descend_ms", C.c_double), ("ema_ms", C.c_double),
-                ("descend_launches", C.c_uint64), ("pack_ms", C.c_double), ("d2h_ms", C.c_double), ("push_ms", C.c_double)]
+                ("descend_launches", C.c_uint64), ("pack_ms", C.c_double), ("d2h_ms", C.c_double), ("push_ms", C.c_double),
+                ("scatter_ms", C.c_double)]
 
 
 _lib = None
@@ -109,6 +110,7 @@ def lib():
     L.shx_upload.argtypes = [vp, vp, sz]
     L.shx_download.argtypes = [vp, vp, sz, C.c_uint]
     L.shx_download_async.argtypes = [vp, vp, sz, C.c_uint]
+    L.shx_download_compact.argtypes = [vp, vp, sz, C.c_int]
     L.shx_erode.argtypes = [vp, C.c_int, u64, C.POINTER(Stats)]
     L.shx_erode_async.argtypes = [vp, C.c_int, u64]
     L.shx_read_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -265,6 +267,11 @@ class World:
             out = np.zeros(self.ncells, CELL_DTYPE)
         fn = self.L.shx_download_async if asynchronous else self.L.shx_download
         self._check(fn(self._h, out.ctypes.data, out.size, mask))
+        return out
+
+    def download_compact(self, out, nthreads=0):
+        """height / discharge / momentum of the owned cells into the first 16 bytes of out's records (the rest untouched)"""
+        self._check(self.L.shx_download_compact(self._h, out.ctypes.data, out.size, nthreads))
         return out
 
     def download_raw(self):

@@ -5,8 +5,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <chrono>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "shx_kernels.cuh"
@@ -118,6 +121,11 @@ struct shx_ctx {
   unsigned* d_veg_totals = nullptr;
   unsigned* h_veg_totals = nullptr;  // pinned
   bool root_counts_valid = false;    // the integer root counts mirror the fp32 rootdensity of every cell
+  // shx_download_compact: 16 bytes per owned cell on the device, a ring of pinned chunks on the host
+  float4* d_compact = nullptr;
+  char* h_ring = nullptr;  // pinned, kRingSlots chunks
+  cudaEvent_t ev_ring[8] = {};
+  double scatter_ms = 0.0;  // host time spent in the scatter since the last shx_timing_read
 };
 
 static StepParams step_params(const shx_params& p) {
@@ -216,6 +224,10 @@ void shx_destroy(shx_ctx* c) {
   if (c->h_stats) cudaFreeHost(c->h_stats);
   if (c->h_flags) cudaFreeHost(c->h_flags);
   for (int i = 0; i < 2; i++) { cudaFree(c->d_plant_pos[i]); cudaFree(c->d_plant_size[i]); }
+  cudaFree(c->d_compact);
+  if (c->h_ring) cudaFreeHost(c->h_ring);
+  for (cudaEvent_t e : c->ev_ring)
+    if (e) cudaEventDestroy(e);
   cudaFree(c->d_veg_flags); cudaFree(c->d_veg_child); cudaFree(c->d_veg_grown); cudaFree(c->d_veg_blocks); cudaFree(c->d_veg_totals);
   if (c->h_veg_totals) cudaFreeHost(c->h_veg_totals);
   delete c;
@@ -573,6 +585,107 @@ int shx_download_async(shx_ctx* c, shx_cell* pool, size_t ncells, unsigned mask)
     if (used[b]) CU(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
   CU(cudaGetLastError());
   return SHX_OK;
+}
+
+// Download of what host code reads after World::erode, in half the PCIe bytes: {height, discharge, momentumx,
+// momentumy} are the FIRST 16 bytes of a quad::cell (cellpool.h:207-220).  One kernel packs them densely (16 bytes per
+// owned cell, pool order), the copy engine streams the dense buffer chunk by chunk into a ring of pinned host chunks,
+// and `nthreads` host threads scatter every chunk into the caller's 32-byte records as it lands (the strided 16-of-32
+// byte DMA straight into the pool measured 2x SLOWER than whole records).  The *_track words (scratch of the erode
+// call, zeroed first thing by the next one, world.h:56-61) and rootdensity (host-owned) are left as they are.
+// Whether this beats the whole-record download depends on the host's memory bandwidth (every record costs a
+// read-for-ownership of its cache line, and that traffic slows the DMA down): measured on a 16-core B200 host, 8192^2:
+// 52.3 ms per frame against 51.7 with whole records -- no gain there, hence opt-in (shx::Bridge::set_download_mode).
+int shx_download_compact(shx_ctx* c, shx_cell* pool, size_t ncells, int nthreads) {
+  if (!c || !pool) return fail(SHX_ERR_ARG, "null argument");
+  if (ncells != (size_t)c->size * c->size) return fail(SHX_ERR_ARG, "pool size does not match the geometry");
+  CU(cudaSetDevice(c->cfg.device));
+  const int ts = c->p.tilesize, ms = c->p.mapsize;
+  if (c->m.row0 % ts || c->m.row1 % ts) return fail(SHX_ERR_ARG, "compact download needs strips of whole tile rows");
+  constexpr int kRingSlots = 8;
+  const size_t chunk_cells = (size_t)1 << 18;  // 4 MiB of 16-byte records per chunk
+  const size_t first_cell = (size_t)(c->m.row0 / ts) * ms * ts * ts;  // owned nodes are contiguous in the pool
+  const size_t n = c->owned_cells;
+  if (!c->d_compact) {
+    if (cudaMalloc((void**)&c->d_compact, n * sizeof(float4)) != cudaSuccess ||
+        cudaMallocHost((void**)&c->h_ring, kRingSlots * chunk_cells * sizeof(float4)) != cudaSuccess) {
+      cudaGetLastError();
+      cudaFree(c->d_compact);
+      c->d_compact = nullptr;
+      return fail(SHX_ERR_NOMEM, "allocation of the compact download buffers failed");
+    }
+    for (int i = 0; i < kRingSlots; i++) CU(cudaEventCreateWithFlags(&c->ev_ring[i], cudaEventDisableTiming));
+  }
+  if (!c->copy_stream) CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  { const int rc_s = span_begin(c, 3); if (rc_s) return rc_s; }
+  pack_fields16_kernel<<<grid_for(c, n), 256, 0, c->stream>>>(c->m, sequential(c) ? 1 : 0, ts, ms, first_cell, n, c->d_compact);
+  { const int rc_s = span_end(c); if (rc_s) return rc_s; }
+  c->launches++;
+  CU(cudaGetLastError());
+  cudaEvent_t packed;
+  CU(cudaEventCreateWithFlags(&packed, cudaEventDisableTiming));
+  CU(cudaEventRecord(packed, c->stream));
+  CU(cudaStreamWaitEvent(c->copy_stream, packed, 0));
+  cudaEventDestroy(packed);  // released once the wait has consumed it
+
+  const size_t nchunks = (n + chunk_cells - 1) / chunk_cells;
+  const int T = std::max(1, std::min(nthreads > 0 ? nthreads : (int)std::thread::hardware_concurrency(), 64));
+  auto enqueue = [&](size_t k) -> int {
+    const size_t cells = std::min(chunk_cells, n - k * chunk_cells);
+    const int slot = (int)(k % kRingSlots);
+    { const int rc_s = span_begin(c, 4, c->copy_stream, true); if (rc_s) return rc_s; }
+    CU(cudaMemcpyAsync(c->h_ring + (size_t)slot * chunk_cells * sizeof(float4), c->d_compact + k * chunk_cells, cells * sizeof(float4),
+                       cudaMemcpyDeviceToHost, c->copy_stream));
+    { const int rc_s = span_end(c, c->copy_stream, true); if (rc_s) return rc_s; }
+    CU(cudaEventRecord(c->ev_ring[slot], c->copy_stream));
+    return SHX_OK;
+  };
+  for (size_t k = 0; k < std::min<size_t>(nchunks, kRingSlots); k++) {
+    const int rc = enqueue(k);
+    if (rc) return rc;
+  }
+  // worker t scatters the cells [t, t + T, ...) x 4096-cell runs of every chunk; chunk k may be read once `ready` > k
+  std::atomic<long> ready{0};
+  std::vector<std::atomic<long>> progress(T);
+  for (auto& p : progress) p.store(0);
+  shx_cell* const dst0 = pool + first_cell;
+  const char* const ring = c->h_ring;
+  auto scatter_share = [&](int t, size_t k) {
+    const size_t cells = std::min(chunk_cells, n - k * chunk_cells);
+    const float4* src = reinterpret_cast<const float4*>(ring + (k % kRingSlots) * chunk_cells * sizeof(float4));
+    shx_cell* dst = dst0 + k * chunk_cells;
+    constexpr size_t kRun = 4096;
+    for (size_t r0 = (size_t)t * kRun; r0 < cells; r0 += (size_t)T * kRun) {
+      const size_t r1 = std::min(cells, r0 + kRun);
+      for (size_t i = r0; i < r1; i++) memcpy(dst + i, src + i, sizeof(float4));  // first half of the 32-byte record
+    }
+  };
+  auto worker = [&](int t) {
+    for (size_t k = 0; k < nchunks; k++) {
+      while (ready.load(std::memory_order_acquire) <= (long)k) std::this_thread::yield();
+      scatter_share(t, k);
+      progress[t].store((long)k + 1, std::memory_order_release);
+    }
+  };
+  std::vector<std::thread> pool_threads;
+  for (int t = 1; t < T; t++) pool_threads.emplace_back(worker, t);
+  int rc = SHX_OK;
+  const auto t_host0 = std::chrono::steady_clock::now();
+  for (size_t k = 0; k < nchunks; k++) {
+    if (cudaEventSynchronize(c->ev_ring[k % kRingSlots]) != cudaSuccess) rc = fail(SHX_ERR_CUDA, "device-to-host copy failed");
+    ready.store((long)k + 1, std::memory_order_release);  // (on failure too: the workers must run to the end)
+    scatter_share(0, k);
+    progress[0].store((long)k + 1, std::memory_order_release);
+    if (k + kRingSlots < nchunks && rc == SHX_OK) {  // the slot of chunk k is free once every worker has left it
+      for (int t = 1; t < T; t++)
+        while (progress[t].load(std::memory_order_acquire) <= (long)k) std::this_thread::yield();
+      rc = enqueue(k + kRingSlots);
+    }
+  }
+  if (rc != SHX_OK) ready.store((long)nchunks + 1, std::memory_order_release);
+  for (auto& th : pool_threads) th.join();
+  c->scatter_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
+  return rc;
 }
 
 int shx_download(shx_ctx* c, shx_cell* pool, size_t ncells, unsigned mask) {
@@ -992,6 +1105,8 @@ int shx_timing_read(shx_ctx* c, shx_timing* out) {
     cudaEventDestroy(s.e1);
   }
   c->spans.clear();
+  out->scatter_ms = c->scatter_ms;
+  c->scatter_ms = 0.0;
   return SHX_OK;
 }
 

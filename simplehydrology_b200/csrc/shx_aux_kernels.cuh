@@ -186,6 +186,24 @@ __global__ void pack_tile_kernel(const TileArgs a, shx_cell* __restrict__ aos) {
   }
 }
 
+// The fields host code reads after World::erode -- {height, discharge, momentumx, momentumy}, the first 16 bytes of a
+// quad::cell -- of every owned cell, 16 bytes per cell in POOL order (node by node, x-major inside a node): the dense
+// stream of shx_download_compact.  first_node: pool index of the first owned node; thread per cell, coalesced stores.
+__global__ void pack_fields16_kernel(const MapView m, int sequential, int tilesize, int mapsize, size_t first_cell, size_t ncells,
+                                     float4* __restrict__ out) {
+  const size_t tile = (size_t)tilesize * tilesize;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncells; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t p = first_cell + i;  // pool index
+    const size_t node = p / tile, in = p % tile;
+    const int x = (int)(node / (size_t)mapsize) * tilesize + (int)(in / (size_t)tilesize);
+    const int y = (int)(node % (size_t)mapsize) * tilesize + (int)(in % (size_t)tilesize);
+    const size_t c = (size_t)(x - m.xlo) * m.size + y;
+    const float4 f = __ldg(reinterpret_cast<const float4*>(m.rec + c));
+    const int hv = __ldg(reinterpret_cast<const int*>(m.hq + c));
+    out[i] = make_float4(sequential ? __int_as_float(hv) : h_to_float(hv), f.x, f.y, f.z);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Plant::root stamps (vegetation.h:87-118).  Applied by ONE thread in list order so that several
 // stamps on one cell add up in the same fp32 order as the host's sequential `+=`.

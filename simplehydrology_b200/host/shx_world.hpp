@@ -18,6 +18,7 @@
 // unchanged.  Errors: the reference reports none; the bridge throws std::runtime_error for misuse
 // of the boundary or CUDA failures (there is no CPU fallback to degrade to).
 #pragma once
+#include <chrono>
 #include <cstdint>
 #include <cstring>
 #include <stdexcept>
@@ -203,11 +204,39 @@ class Bridge {
     if (!val_.empty()) mcheck(shx_multi_set_rootdensity(multi_, xy_.data(), val_.data(), val_.size()), "shx_multi_set_rootdensity");
     shx_stats st;
     mcheck(shx_multi_erode(multi_, cycles, seed, &st), "shx_multi_erode");
-    // Whole records: one contiguous DMA per tile.  (Selecting height/discharge/momentum only makes it a
-    // strided 16-of-32-byte copy, measured 2x SLOWER at 8192^2.)  rootdensity comes back as pushed above;
-    // the *_track fields are scratch of the erode call (world.h:56-61 zeroes them first thing).
-    mcheck(shx_multi_download(multi_, pool_, ncells_, SHX_F_ALL), "shx_multi_download");
+    download();
     return st;
+  }
+
+  // What comes back per frame.  kRecords: the whole 32-byte records, one contiguous DMA per tile (a strided
+  // 16-of-32-byte DMA measured 2x SLOWER at 8192^2).  kCompact (one GPU): {height, discharge, momentumx, momentumy} --
+  // everything host code reads after World::erode; rootdensity is the host's own, the *_track fields are scratch of
+  // the call (world.h:56-61 zeroes them first thing) -- as a dense 16-byte stream scattered into the pool by host
+  // threads (shx_download_compact): half the PCIe bytes, but every record costs the host a read-for-ownership.
+  // Measured on the B200 boxes of this project (16 host cores): 52.3 ms per 8192^2 frame compact against 51.7 with
+  // records -- the host scatters no faster than PCIe saves, and its memory traffic slows the DMA down -- so kRecords
+  // is the default.  kAuto: frame 0 downloads records, frame 1 the compact stream, the faster one serves from then on
+  // (the compact probe frame also pays the one-time allocation of its buffers).
+ public:
+  enum DownloadMode { kAuto = 0, kRecords = 1, kCompact = 2 };
+  void set_download_mode(DownloadMode m) { mode_ = m; }
+  DownloadMode download_mode() const { return mode_; }  // kAuto until the second frame has decided
+  double last_download_ms() const { return last_download_ms_; }
+
+ private:
+  void download() {
+    const auto t0 = std::chrono::steady_clock::now();
+    DownloadMode use = mode_;
+    if (shx_multi_strips(multi_) > 1) use = kRecords;
+    else if (use == kAuto) use = frames_ == 0 ? kRecords : kCompact;
+    if (use == kCompact) check(shx_download_compact(context(), pool_, ncells_, 0), "shx_download_compact");
+    else mcheck(shx_multi_download(multi_, pool_, ncells_, SHX_F_ALL), "shx_multi_download");
+    last_download_ms_ = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (mode_ == kAuto && shx_multi_strips(multi_) == 1) {
+      if (frames_ == 0) records_ms_ = last_download_ms_;
+      else if (frames_ == 1) mode_ = last_download_ms_ < records_ms_ ? kCompact : kRecords;
+    }
+    frames_++;
   }
 
   size_t pool_index(int x, int y) const {  // cellpool.h:327-336, math.h:11-14
@@ -267,6 +296,9 @@ class Bridge {
     }
   }
 
+  DownloadMode mode_ = kRecords;
+  unsigned long long frames_ = 0;
+  double records_ms_ = 0.0, last_download_ms_ = 0.0;
   shx_cell* pool_;
   size_t ncells_ = 0;
   shx_multi* multi_ = nullptr;

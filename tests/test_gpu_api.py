@@ -186,3 +186,40 @@ def test_cpp_host_adaptor_equals_the_python_path(tmp_path, init_cells):
             W.download(out=host, mask=shx.F_ALL)
     assert np.array_equal(got.view(np.uint8), host.view(np.uint8))
     assert "total steps" in r.stdout
+
+
+@pytest.mark.parametrize("mapsize,nthreads", [(1, 1), (2, 3), (4, 0)])
+def test_download_compact_equals_the_first_half_of_the_records(mapsize, nthreads):
+    """shx_download_compact: {height, discharge, momentumx, momentumy} of every cell, bit for bit what shx_download
+    brings, scattered into the first 16 bytes of the pool's records by host threads; tracks and rootdensity untouched"""
+    with shx.World(mapsize=mapsize) as W:
+        W.init_terrain(3)
+        for _ in range(2):
+            W.erode(256, seed=5)
+        full = W.download()
+        pool = np.zeros(full.size, shx.CELL_DTYPE)
+        for f in ("discharge_track", "momentumx_track", "momentumy_track", "rootdensity"):
+            pool[f] = 7.5  # must survive
+        pool["height"] = -1.0
+        W.download_compact(pool, nthreads)
+    for f in ("height", "discharge", "momentumx", "momentumy"):
+        assert np.array_equal(pool[f].view(np.uint32), full[f].view(np.uint32)), f
+    for f in ("discharge_track", "momentumx_track", "momentumy_track", "rootdensity"):
+        assert np.all(pool[f] == 7.5), f
+    assert float(np.abs(full["discharge"]).max()) > 0.0
+
+
+def test_download_compact_of_a_strip_fills_only_its_own_tiles():
+    with shx.World(mapsize=4, row0=512, row1=1536, halo=2) as W:
+        W.synth_terrain(2)
+        W.erode(64, seed=1)
+        full = np.zeros(W.ncells, shx.CELL_DTYPE)
+        W.download(out=full)
+        pool = np.zeros(W.ncells, shx.CELL_DTYPE)
+        pool["height"] = -1.0
+        W.download_compact(pool, 4)
+    tile = 512 * 512
+    own = slice(4 * tile, 12 * tile)  # tile rows 1 and 2 of four
+    for f in ("height", "discharge", "momentumx", "momentumy"):
+        assert np.array_equal(pool[f][own].view(np.uint32), full[f][own].view(np.uint32)), f
+    assert np.all(pool["height"][:4 * tile] == -1.0) and np.all(pool["height"][12 * tile:] == -1.0)
