@@ -124,7 +124,7 @@ typedef struct {
                           SHX_ERR_CAPACITY rather than splitting elsewhere */
   int variant;         /* one thread per drop, register budget: 0 = 64 (1024 threads/SM), 1 = 128 (512/SM), 2 = 72 (7x128/SM),
                           3 = 72 (2x448/SM); 5 = eight lanes per drop (what the library picks for batches of up to
-                          4 096 drops) in CTAs of block_threads */
+                          6 144 drops) in CTAs of block_threads */
   int keep_tracks;     /* 0: erode's EMA pass also zeroes the *_track accumulators (the reset the reference
                           does at the START of the next call, world.h:56-61, hoisted into the same pass);
                           1: leave them readable after erode, at the cost of one more pass per call */

@@ -25,7 +25,7 @@ struct LaunchShape {
 };
 
 constexpr size_t kDropsPerLaunch = 131072;  // drops that march together in one launch (device-independent split)
-constexpr size_t kShapeLimit[3] = {4096, 24576, 49152};  // largest batch of launch shapes [0], [1], [2] (see shx_create)
+constexpr size_t kShapeLimit[3] = {6144, 24576, 49152};  // largest batch of launch shapes [0], [1], [2] (see shx_create)
 
 struct TimingSpan {
   int kind;  // 0 spawn, 1 descend, 2 ema, 3 pack (download), 4 device-to-host copy, 5 rootdensity push
@@ -362,7 +362,7 @@ int shx_create(shx_ctx** out, const shx_params* p, const shx_config* cfg_in) {
     return fail(SHX_ERR_ARG, "peer mode does not take launch-shape overrides");
   }
   // Launch shapes, chosen by batch size (kShapeLimit; measured with the L2 hints on the REDs, profiles/r2_l2_hints.txt):
-  // [0] eight lanes per drop in CTAs of 256 (32 drops): up to 4 096 drops, the reference's default call; one thread
+  // [0] eight lanes per drop in CTAs of 128 (16 drops): up to 6 144 drops, the reference's default call; one thread
   // per drop beyond, all with the cooperative gather at 72 registers: [1] CTAs of 64 (up to 24 576 drops: a 2048^2
   // world, the strips of an eight-GPU run), [2] CTAs of 128 (up to 49 152: a 4096^2 world, the strips of a four-GPU
   // run), [3] "dense", 2 x 448 threads per SM (the 8192^2 cycle).  An explicit block_threads / variant / coop /
@@ -381,7 +381,7 @@ int shx_create(shx_ctx** out, const shx_params* p, const shx_config* cfg_in) {
       ls.kernel = big_kernel(ls.block, cfg.variant, cfg.coop == 1);
     } else if (i == 0 && !peer) {
       ls.lanes = 8;
-      ls.block = 256;
+      ls.block = 128;  // 16 drops per CTA: 512 drops cover 32 SMs (CTAs of 256: 4.50 us per phase, of 64-128: 4.38)
       ls.kernel = (const void*)descend_group_kernel<256, 4>;
     } else if (i <= 2) {
       ls.block = i == 2 ? 128 : 64;
@@ -1014,8 +1014,10 @@ static int run_device_drops(shx_ctx* c, size_t n, bool trace, bool align_age = f
     a.claim_epoch = c->claim_epoch;
     void* args[] = {&a};
     size_t take;
-    if (left <= 128 && !c->forced_shape) {
-      // a handful of drops: one CTA of eight lanes per drop, the per-phase barrier is a plain __syncthreads
+    if (left <= 16 && !c->forced_shape) {
+      // a handful of drops: one CTA of eight lanes per drop, the per-phase barrier is a plain __syncthreads.  (Only
+      // for a CTA of up to 128 threads: 128 drops in ONE CTA of 1024 threads measured 4.73 us per phase, the same
+      // drops in 16 CTAs on 16 SMs behind the grid barrier 4.20.)
       take = left;
       a.ndrops = (unsigned)take;
       const int block = (int)((take * 8 + 31) / 32 * 32);

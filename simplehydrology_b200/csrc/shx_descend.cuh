@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_group_kernel(
   if (alive) claim(cell_of(d.px, d.py), 0, 1u);  // every drop that is awake in phase 0 claims its cell (tag 1, parity 0)
   {
     const unsigned block_sum = (unsigned)__syncthreads_count(alive || asleep);
-    grid_barrier_sum(a.bar, 0u, block_sum, &s_total, s_hi[0], s_hi[1]);
+    grid_barrier_sum<true>(a.bar, 0u, block_sum, &s_total, s_hi[0], s_hi[1]);
   }
 
   for (unsigned phase = 0;; ++phase) {
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) descend_group_kernel(
     }
 
     const unsigned block_sum = (unsigned)__syncthreads_count(alive || asleep || (dC_prev | pend_val));
-    if (grid_barrier_sum(a.bar, phase + 1u, block_sum, &s_total, s_hi[0], s_hi[1]) == 0u) break;
+    if (grid_barrier_sum<true>(a.bar, phase + 1u, block_sum, &s_total, s_hi[0], s_hi[1]) == 0u) break;
     if (phase + 3u >= kMaxPhases) {  // the claim tag would wrap: give up (the host reports SHX_ERR_RANGE)
       if (blockIdx.x == 0 && tid == 0) atomicOr(a.abort_flag, 2);
       break;

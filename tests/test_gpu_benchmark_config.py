@@ -76,7 +76,7 @@ def test_default_launch_is_bit_exact_at_benchmark_size(mapsize, terrain16, ref_j
         grid, block, lanes = W.launch_info()
         h0, h1, f, t = W.download_raw()
     # the shapes bench.py times, all one thread per drop: 8192^2 -> 293 CTAs of 448; 4096^2 (the batch of one strip of
-    # a four-GPU run) -> 256 CTAs of 128; 2048^2 -> 128 CTAs of 64.  (Eight lanes per drop serve batches of up to 4 096
+    # a four-GPU run) -> 256 CTAs of 128; 2048^2 -> 128 CTAs of 64.  (Eight lanes per drop serve batches of up to 6 144
     # drops: tests/test_gpu_batched.py and the 512^2 tests.)
     assert (grid, block, lanes) == {16: (293, 448, 1), 8: (256, 128, 1), 4: (128, 64, 1)}[mapsize]
     assert np.array_equal(h0, ls.height_q(0)) and np.array_equal(h1, ls.height_q(1))
