@@ -151,8 +151,8 @@ static int grid_for(const shx_ctx* c, size_t n, int block = 256) {
 }
 
 
-// Instantiations {max CTA threads, min CTAs/SM}.  KERNEL_SMALL: one CTA of up to 1024 threads for
-// small batches (the barrier is a plain __syncthreads).  Multi-CTA: the first four cap registers at
+// Instantiations {max CTA threads, min CTAs/SM}.  KERNEL_SMALL: the eight-lane kernel as ONE CTA (the barrier is a
+// plain __syncthreads): batches of up to 16 drops, and the 1024-thread shape the tests force.  Multi-CTA: the first four cap registers at
 // 64 (1024 threads per SM); variant 1 allows 128 registers (512 threads per SM); variant 2 is
 // 7 CTAs of 128 threads per SM = 896 threads at 72 registers, just enough for the 886 drops per SM
 // of an 8192^2 cycle.
