@@ -85,3 +85,26 @@ def test_trace_of_a_drop_outside_the_map_is_empty(init_cells):
         assert len(W.trace_drop(-5.0, 10.0)) == 0  # water.h:62-68
         assert len(W.trace_drop(10.0, 512.0)) == 0
         assert len(W.trace_drop(-0.5, -0.5)) >= 1   # truncates to cell (0,0): in bounds
+
+
+def test_spawn_rejection_sees_what_earlier_drops_of_the_call_left():
+    """world.h:71-74 tests `height < 0.1` when each drop is CREATED, i.e. after the earlier drops of the same call
+    have run (round-1 advisor finding).  A cell just above 0.1 on a slope: the first drop spawned there erodes it
+    below 0.1, the second spawn on the same cell must be rejected."""
+    p = orc.default_params(1)
+    p.tilesize = 64
+    y = np.arange(64, dtype=np.float32)
+    h = np.tile(np.float32(0.1003) + np.float32(0.004) * (np.float32(32.0) - y), (64, 1)).astype(np.float32)  # falls along +y
+    cells = orc.planar_to_tiled(p, h)
+    xy = np.array([[32.0, 32.0], [32.0, 32.0], [10.0, 20.0]], np.float32)
+    want = cells.copy()
+    so = orc.Seq(want, p, erf_poly=True).erode_spawnlist(xy)
+    assert (so.spawned, so.rejected) == (2, 1)  # the restatement follows the reference: second spawn on (32, 32) rejected
+    assert want["height"][orc.lib().orc_tiled_index(p, 32, 32)] < np.float32(0.1) <= cells["height"][orc.lib().orc_tiled_index(p, 32, 32)]
+    with shx.World(params=shx.Params.from_buffer_copy(bytes(p)), mode=shx.MODE_SEQUENTIAL) as W:
+        W.upload(cells)
+        st = W.erode_spawnlist(xy)
+        got = W.download()
+    assert (st.spawned, st.rejected, st.steps) == (so.spawned, so.rejected, so.steps)
+    for f in ("height", "discharge", "momentumx", "momentumy"):
+        assert np.array_equal(bits(got[f]), bits(want[f])), f
