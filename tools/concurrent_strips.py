@@ -7,7 +7,7 @@ from simplehydrology_b200 import strips
 
 MS, CYC = 16, 512
 import itertools
-for k, kw in itertools.product((1, 2, 4, 8, 16), ({}, dict(block_threads=448, variant=3, coop=1), dict(block_threads=128, variant=2, coop=1))):
+for k, kw in itertools.product((1, 2, 4, 8), ({}, dict(block_threads=448, variant=3, coop=1), dict(block_threads=128, variant=2, coop=1))):
     if k == 1 and kw: continue
     streams = [torch.cuda.Stream() for _ in range(k)]
     bs = []
