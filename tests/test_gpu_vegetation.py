@@ -41,7 +41,9 @@ def test_grow_is_bit_identical_to_the_oracle_coupled_with_erosion():
     with W:
         # a standing population first (the reference needs ~100 frames to get going): 400 plants on a grid
         g = np.arange(4, 124, 6)
-        seedlings = np.array([[x, y, 0.1 * ((x + y) % 7)] for x in g for y in g], np.float32)
+        seedlings = np.array([[x, y, 0.1 * ((x + y) % 7)] for x in g for y in g] +
+                             [[0, 0, 0.3], [127, 127, 0.2], [0, 64, 0.1], [64, 127, 0.5], [127, 0, 0.0]], np.float32)  # corners and
+        # edges: Plant::root skips the cells that do not exist (getCell == NULL, vegetation.h:91-120)
         W.veg_upload(seedlings, stamp_roots=True)
         ls.veg_upload(seedlings, stamp_roots=True)
         same_state(W, ls)
