@@ -535,6 +535,38 @@ def run_cuda(args):
                                           "unit": UNIT, "note": "per-GPU cells and spawned drops as at N = 1 on 8192^2; compare value / 4 with the N = 1 line. A strip's batch is its 131 072 spawned drops "
                                                   "PLUS the drops its neighbours handed over, and a launch holds at most 131 072: every call pays a second, latency-bound launch"}
 
+    # ---- BASELINE configs[4]: erosion coupled with the vegetation's rootdensity feedback and the vertex-pool update,
+    # the whole frame on the device (SimpleHydrology.cpp:319-335: erode, Vegetation::grow, updatenode, tree models)
+    if world == 1:
+        with shx.World(mapsize=1) as Wc:
+            Wc.set_stream(torch.cuda.current_stream().cuda_stream)
+            Wc.init_terrain(SEED)
+            Wc.veg_create(1 << 16)
+            vb = torch.empty(512 * 512 * 12, dtype=torch.float32, device=dev)
+            tm_buf = torch.empty((1 << 16) * 16, dtype=torch.float32, device=dev)
+
+            def frame(f):
+                Wc.erode_async(CYCLES, SEED)
+                Wc.veg_grow(SEED, f)  # reads back 20 bytes of counters (the host needs the plant count)
+                Wc.vertex_fill(vb.data_ptr())
+                Wc.veg_tree_models(tm_buf.data_ptr())
+
+            for f in range(250):
+                frame(f)
+            torch.cuda.synchronize()
+            t0_c = time.perf_counter()
+            for f in range(250, 300):
+                frame(f)
+            torch.cuda.synchronize()
+            dt_c = (time.perf_counter() - t0_c) / 50
+            line["configs"]["coupled_512"] = {
+                "map": "512x512", "frame": "shx_erode(512) + shx_veg_grow + shx_vertex_fill + shx_veg_tree_models, all on the device",
+                "frames": 300, "timed": "frames 250-299 (host wall clock, one 20-byte read-back per frame)", "ms_per_frame": 1e3 * dt_c,
+                "frames_per_s": 1.0 / dt_c, "plants": Wc.veg_count(),
+                "note": "the reference's own frame (World::erode + Vegetation::grow + updatenode on one core) takes ~85 ms at this size "
+                        "(tests/test_gpu_coupled.py runs the 300-frame comparison: 4 001 plants there)"}
+            del vb, tm_buf
+
     # ---- e2e: the C++ host adaptor's own frame on a HOST pool (rank 0 drives all N GPUs from one thread through
     # shx_multi; the other ranks wait on the rendezvous store, not in a GPU kernel, so their devices are free)
     if world > 1:
